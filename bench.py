@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py — DIB-R fwd+bwd throughput on B200 (BASELINE.json metric).
+
+    python bench.py --gpus N --steps K --warmup W          # this repo's kernels
+    python bench.py --impl reference --gpus N ...          # reference arm (CPU path)
+
+Workload (`config.workload` = "c4_shard"): the per-GPU shard of BASELINE.json
+configs[3] — 32 views per GPU of a ~20k-face mesh (icosphere level 5 = 20480
+faces, jittered, random rotation and camera; SURVEY.md §8d generator G1) at
+1024x1024, D = 3 feature channels, fp32.  One "step" = dibr_rasterization forward
++ backward (grads wrt face_vertices_image and face_features) over the shard;
+with N > 1 every rank renders its own 32 views (weak scaling) and the per-view
+gradients are all-gathered with NCCL.  Prints ONE JSON line on rank 0.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "DIB-R fwd+bwd Mpixels/sec at 1024^2 per GPU; achieved HBM GB/s vs peak"
+UNIT = "Mpixels/s"
+WORKLOADS = {
+    # name: (views per GPU, icosphere level, H, W, D)
+    "c4_shard": (32, 5, 1024, 1024, 3),
+    "c2": (8, 4, 256, 256, 3),
+    "c3": (64, 5, 512, 512, 3),
+    "tiny": (2, 3, 128, 128, 3),
+}
+SIGMAINV, BOXLEN, KNUM, MULT, EPS = 7000.0, 0.02, 30, 1000.0, 1e-8
+
+
+def parse():
+    p = argparse.ArgumentParser()
+    p.add_argument("--gpus", type=int, default=1)
+    p.add_argument("--steps", type=int, default=20)
+    p.add_argument("--warmup", type=int, default=5)
+    p.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    p.add_argument("--workload", default="c4_shard", choices=list(WORKLOADS))
+    p.add_argument("--cpu-seconds", type=float, default=20.0,
+                   help="CPU work budget for the cpu_baseline sample")
+    p.add_argument("--no-cpu-baseline", action="store_true")
+    p.add_argument("--no-ref-cuda", action="store_true")
+    p.add_argument("--ref-cuda-views", type=int, default=2)
+    return p.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            d = json.load(open(path))
+            return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def algorithmic_bytes(B, F, H, W, D, s=4):
+    """compulsory HBM traffic of the fused path (fp32: s = 4)."""
+    P = B * H * W
+    fwd = P * (D * s + 4 + 8 + 12) + B * F * (12 + 24 + 3 * D * s)
+    bwd = P * (D * s + 4 + 8 + 12) + B * F * (48 + 6 * D * s)
+    bwd_raster = P * (D * s + 8 + 12) + B * F * (24 + 3 * D * s + 24 + 3 * D * s)
+    return {"fwd": fwd, "bwd": bwd, "total": fwd + bwd, "bwd_raster": bwd_raster}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in out.strip().splitlines():
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": statistics.median(sm) if sm else None,
+                "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def make_scene(workload, rank):
+    from kaolin_b200 import synthetic
+    B, level, H, W, D = WORKLOADS[workload]
+    fvz, fvi, fnz = synthetic.icosphere_views(B, level, seed=1234 + 17 * rank)
+    ff = synthetic.random_features(B, fvz.shape[1], D, seed=99 + rank)
+    return B, fvz.shape[1], H, W, D, fvz, fvi, fnz, ff
+
+
+# ---------------------------------------------------------------------------
+def cpu_sample(workload, budget_s, threads=None):
+    """Oracle (CPU restatement of the reference kernels) on a bounded sample:
+    a centred strip of rows of ONE view of the workload, all host threads."""
+    import oracle
+    oracle.build()
+    B, F, H, W, D, fvz, fvi, fnz, ff = make_scene(workload, 0)
+    fvz, fvi, fnz, ff = fvz[:1], fvi[:1], fnz[:1], ff[:1]
+    rng = np.random.default_rng(0)
+    g_feat = rng.uniform(size=(1, H, W, D)).astype(np.float32)
+    g_soft = rng.uniform(size=(1, H, W)).astype(np.float32)
+    if threads:
+        oracle.set_threads(threads)
+    cores = threads or oracle.max_threads()
+
+    def strips_for(nblocks, rows_per_block=4):
+        nblocks = max(1, min(H // rows_per_block, nblocks))
+        pitch = H / nblocks                      # blocks spread evenly over the image height
+        return [(int(i * pitch), int(i * pitch) + rows_per_block) for i in range(nblocks)]
+
+    probe = strips_for(4)
+    s = oracle.RowSample(H, W, fvz, fvi, ff, fnz, g_feat, g_soft, 0, 0, SIGMAINV, BOXLEN, KNUM, MULT, EPS,
+                         strips=probe)
+    s.run()                                       # touch pages, start the OpenMP team
+    t = time.perf_counter(); s.run(); dt = time.perf_counter() - t
+    nblocks = int(max(4, len(probe) * budget_s / max(dt, 1e-6)))
+    strips = strips_for(nblocks)
+    s = oracle.RowSample(H, W, fvz, fvi, ff, fnz, g_feat, g_soft, 0, 0, SIGMAINV, BOXLEN, KNUM, MULT, EPS,
+                         strips=strips)
+    rows = sum(b - a for a, b in strips)
+    return s, cores, (f"{rows} of {H} rows ({len(strips)} evenly spaced 4-row blocks) of 1 view of "
+                      f"{workload} ({W}x{H}, {F} faces)")
+
+
+def run_reference(args):
+    """Reference arm: the reference has no CPU implementation of this path
+    (rasterization.cpp:95-102 raises without CUDA), so this times the oracle port
+    (kind "port") on the host cores; rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    per_step = max(0.5, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    s, cores, desc = cpu_sample(args.workload, per_step)
+    for _ in range(args.warmup):
+        s.run()
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        s.run()
+    dt = (time.perf_counter() - t) / max(1, args.steps)
+    val = s.pixels / dt / 1e6
+    B, level, H, W, D = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "views_per_gpu": B, "faces_per_view": 20 * 4 ** level,
+                   "height": H, "width": W, "feat_dim": D, "knum": KNUM, "sample": desc},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from kaolin_b200 import _lib
+    from kaolin_b200.render.mesh import _host, dibr_rasterization
+    from kaolin_b200.multi_gpu import all_gather_view_grads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (impl=ours) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    B, F, H, W, D, fvz, fvi, fnz, ff = make_scene(args.workload, rank)
+    pin = lambda a: torch.from_numpy(a).pin_memory()
+    h_fvz, h_fvi, h_fnz, h_ff = pin(fvz), pin(fvi), pin(fnz), pin(ff)
+    d_fvz, d_fvi, d_fnz, d_ff = (t.to(dev) for t in (h_fvz, h_fvi, h_fnz, h_ff))
+    gen = torch.Generator(device=dev); gen.manual_seed(4321 + rank)
+    g_feat = torch.rand((B, H, W, D), device=dev, generator=gen)
+    g_soft = torch.rand((B, H, W), device=dev, generator=gen)
+    boxlen_m = BOXLEN * MULT
+    mode = _lib.RASTER | _lib.SOFT_MASK
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- resident path: C ABI with device pointers (value) ----------------
+    def step_resident(ev=None):
+        if ev: ev[0].record()
+        feat, idx, wts, soft, ws = _host.forward(mode, H, W, d_fvz, d_fvi, d_ff, d_fnz, None, MULT, EPS,
+                                                 SIGMAINV, boxlen_m, KNUM)
+        if ev: ev[1].record()
+        g_fvi, g_ff = _host.backward(H, W, g_feat, g_soft, idx, wts, soft, d_fvi, d_ff, MULT, EPS,
+                                     SIGMAINV, boxlen_m, KNUM, ws, True)
+        if ev: ev[2].record()
+        if world > 1:
+            g_fvi, g_ff = all_gather_view_grads([g_fvi, g_ff], B * world)
+        return g_fvi, g_ff
+
+    for _ in range(args.warmup):
+        step_resident()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
+    start.record()
+    for k in range(args.steps):
+        step_resident(evs[k])
+    end.record()
+    barrier()
+    clocks = sampler.stop()
+    total_ms = start.elapsed_time(end)
+    fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
+    bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+    t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t.item()) / args.steps
+    value = world * B * H * W / (ms_per_step * 1e-3) / 1e6
+
+    # ---- the backward scatter kernel alone (roofline kernel) ---------------
+    feat, idx, wts, soft, ws = _host.forward(mode, H, W, d_fvz, d_fvi, d_ff, d_fnz, None, MULT, EPS,
+                                             SIGMAINV, boxlen_m, KNUM)
+    covered = float((idx >= 0).float().mean().item())
+    rb = [torch.cuda.Event(enable_timing=True) for _ in range(2 * args.steps)]
+    for _ in range(2):
+        _host.backward(H, W, g_feat, None, idx, wts, None, d_fvi, d_ff, MULT, EPS, 0., 0., 0, None, False)
+    torch.cuda.synchronize()
+    for k in range(args.steps):
+        rb[2 * k].record()
+        _host.backward(H, W, g_feat, None, idx, wts, None, d_fvi, d_ff, MULT, EPS, 0., 0., 0, None, False)
+        rb[2 * k + 1].record()
+    torch.cuda.synchronize()
+    raster_bwd_ms = statistics.mean(rb[2 * k].elapsed_time(rb[2 * k + 1]) for k in range(args.steps))
+    del feat, idx, wts, soft, ws
+
+    # ---- e2e: public API, host buffers, H2D + D2H inside the timed region --
+    out_gfvi = torch.empty((B, F, 3, 2), dtype=torch.float32).pin_memory()
+    out_gff = torch.empty((B, F, 3, D), dtype=torch.float32).pin_memory()
+    out_loss = torch.empty((1,), dtype=torch.float32).pin_memory()
+
+    def step_e2e():
+        a_fvz = h_fvz.to(dev, non_blocking=True)
+        a_fvi = h_fvi.to(dev, non_blocking=True).requires_grad_(True)
+        a_ff = h_ff.to(dev, non_blocking=True).requires_grad_(True)
+        a_fnz = h_fnz.to(dev, non_blocking=True)
+        feat, soft, idx = dibr_rasterization(H, W, a_fvz, a_fvi, a_ff, a_fnz, SIGMAINV, BOXLEN, KNUM)
+        torch.autograd.backward([feat, soft], [g_feat, g_soft])
+        g1, g2 = a_fvi.grad, a_ff.grad
+        if world > 1:
+            full = all_gather_view_grads([g1, g2], B * world)
+            g1, g2 = full[0][rank * B:(rank + 1) * B], full[1][rank * B:(rank + 1) * B]
+        out_gfvi.copy_(g1, non_blocking=True)
+        out_gff.copy_(g2, non_blocking=True)
+        out_loss.copy_((soft.sum() / soft.numel()).reshape(1), non_blocking=True)
+        torch.cuda.current_stream().synchronize()     # the host consumes the step's result
+        return float(out_loss[0])
+
+    for _ in range(max(3, args.warmup // 2)):
+        step_e2e()
+    barrier()
+    start.record()
+    for _ in range(args.steps):
+        step_e2e()
+    end.record()
+    barrier()
+    t = torch.tensor([start.elapsed_time(end)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_ms = float(t.item()) / args.steps
+    e2e_value = world * B * H * W / (e2e_ms * 1e-3) / 1e6
+    h2d = sum(x.numel() * x.element_size() for x in (h_fvz, h_fvi, h_fnz, h_ff))
+    d2h = sum(x.numel() * x.element_size() for x in (out_gfvi, out_gff, out_loss))
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peak, peak_src = peaks()
+    A = algorithmic_bytes(B, F, H, W, D)
+    ach = A["bwd_raster"] / (raster_bwd_ms * 1e-3) / 1e9
+    roofline = {
+        "kernel": "raster_bwd_kernel<3> (+2 output memsets) via dibr_b200_rasterize_backward",
+        "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+        "traffic": None, "peak_source": peak_src,
+        "algorithmic_bytes_per_launch": A["bwd_raster"], "ms_per_launch": raster_bwd_ms,
+        "phases": {
+            "forward_ms": fwd_ms, "backward_ms": bwd_ms,
+            "forward_GBps": A["fwd"] / (fwd_ms * 1e-3) / 1e9,
+            "backward_GBps": A["bwd"] / (bwd_ms * 1e-3) / 1e9,
+            "step_GBps": A["total"] / (ms_per_step * 1e-3) / 1e9,
+            "step_frac_of_peak": A["total"] / (ms_per_step * 1e-3) / 1e9 / peak,
+        },
+    }
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.workload, "views_per_gpu": B, "faces_per_view": F, "height": H,
+                   "width": W, "feat_dim": D, "features": "fp32", "knum": KNUM, "sigmainv": SIGMAINV,
+                   "boxlen": BOXLEN, "covered_fraction": covered,
+                   "parallelism": f"views sharded x{world}, NCCL all-gather of per-view grads"
+                   if world > 1 else "single GPU",
+                   "l2": "per-step working set (>1 GB of images) exceeds the 126 MB L2; no flush needed"},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "api": "kaolin_b200.render.mesh.dibr_rasterization + autograd, pinned host buffers"},
+        "gpu_launches": 6 * args.steps,
+        "roofline": roofline,
+        "triangle_pixel_tests_per_s": {
+            "brute_force_equivalent": float(B) * H * W * F * 0.5 / (fwd_ms * 1e-3),
+            "note": "faces x pixels the reference kernel would test (valid ~ F/2) / forward time"},
+    }
+
+    if not args.no_cpu_baseline and world == 1:
+        s, cores, desc = cpu_sample(args.workload, args.cpu_seconds)
+        t0 = time.perf_counter(); s.run(); dt = time.perf_counter() - t0
+        line["cpu_baseline"] = {"value": s.pixels / dt / 1e6, "unit": UNIT, "cores": cores,
+                                "kind": "port", "sample": desc, "seconds": dt}
+    else:
+        line["cpu_baseline"] = None
+
+    if not args.no_ref_cuda and world == 1:
+        line["reference_cuda"] = time_reference_cuda(args, dev, B, F, H, W, D, d_fvz, d_fvi, d_ff, d_fnz,
+                                                     g_feat, g_soft)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def time_reference_cuda(args, dev, B, F, H, W, D, d_fvz, d_fvi, d_ff, d_fnz, g_feat, g_soft):
+    """The reference's own CUDA kernels (oracle/_ref, unmodified sources compiled for sm_100a)
+    on a bounded number of views of the same workload, same GPU — the bar to beat."""
+    import torch
+    try:
+        from oracle import ref_cuda
+        if not ref_cuda.available():
+            return {"unavailable": "oracle/_ref/kaolin_ref_C.so not present"}
+        v = max(1, min(B, args.ref_cuda_views))
+        a = (d_fvz[:v], d_fvi[:v], d_ff[:v], d_fnz[:v], g_feat[:v].contiguous(), g_soft[:v].contiguous())
+        ref_cuda.dibr_forward_backward(H, W, *a, SIGMAINV, BOXLEN, KNUM)
+        torch.cuda.synchronize()
+        n = 3
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        for _ in range(n):
+            ref_cuda.dibr_forward_backward(H, W, *a, SIGMAINV, BOXLEN, KNUM)
+        e.record()
+        torch.cuda.synchronize()
+        ms = s.elapsed_time(e) / n
+        return {"value": v * H * W / (ms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ms,
+                "sample": f"{v} of {B} views, reference wrappers restated in torch (oracle/ref_cuda.py)"}
+    except Exception as exc:  # reported, never fatal for our arm
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

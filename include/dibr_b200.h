@@ -1,0 +1,155 @@
+/*
+ * dibr_b200.h — C ABI of libdibr_b200.so: B200 (sm_100a) kernels for Kaolin's
+ * DIB-R hot path (rasterize + dibr_soft_mask, forward and backward).
+ *
+ * Plain pointers and sizes only; no torch / ATen types.  All pointers are DEVICE
+ * pointers on the current CUDA device unless stated otherwise; all tensors are
+ * dense row-major ("contiguous") fp32 / int64 / uint8 exactly as the reference
+ * operators take them.  Nothing is allocated by the library: the caller passes
+ * the outputs and a scratch `workspace` of at least dibr_b200_workspace_bytes().
+ * Every output is fully written (no pre-zeroing needed).  Calls are asynchronous
+ * on `stream` and never synchronise; they are re-entrant (no global state).
+ *
+ * Return value: 0 on success; DIBR_B200_E* (<0) for argument errors detected on
+ * the host; a positive cudaError_t if a launch failed (cudaGetLastError()).
+ *
+ * The four "operator" entry points replace, one for one, the functions the
+ * reference registers in kaolin/csrc/bindings.cpp:111-115; the two "fused"
+ * entry points implement the same mathematics directly on the public-API
+ * tensors (kaolin/render/mesh/dibr.py:119-209) without the packed temporaries.
+ */
+#ifndef DIBR_B200_H_
+#define DIBR_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DIBR_B200_OK 0
+#define DIBR_B200_EINVAL (-1)      /* null pointer / non-positive size / bad flag */
+#define DIBR_B200_EWORKSPACE (-3)  /* workspace_bytes too small */
+#define DIBR_B200_ESIZE (-4)       /* image larger than 16384 px or index overflow */
+
+#define DIBR_B200_MAX_IMAGE_DIM 16384
+
+/* forward `mode` bits */
+#define DIBR_B200_RASTER 1     /* compute face_idx / weights / features */
+#define DIBR_B200_SOFT_MASK 2  /* compute soft_mask */
+
+typedef struct CUstream_st* dibr_b200_stream_t; /* == cudaStream_t */
+
+int dibr_b200_version(void);
+
+/* Scratch needed by any entry point for `batch` views with `total_faces` faces
+ * in all views together on a height x width image. */
+size_t dibr_b200_workspace_bytes(int batch, int64_t total_faces, int height, int width);
+
+/*
+ * Fused forward on the public-API tensors.
+ * Replaces: kaolin/render/mesh/rasterization.py:273-352 (RasterizeCuda.forward:
+ * valid-face packing, x multiplier, bboxes, op call, index remap) and
+ * kaolin/render/mesh/dibr.py:29-55 (DibrSoftMaskCuda.forward) in one pass.
+ *
+ *  face_vertices_z      (B,F,3)   f32
+ *  face_vertices_image  (B,F,3,2) f32, NOT multiplied
+ *  face_features        (B,F,3,D) f32 (may be NULL when D == 0)
+ *  face_normals_z       (B,F) f32 or NULL: faces with value >= 0 are rasterized
+ *  valid_faces          (B,F) u8  or NULL: faces with non-zero are rasterized
+ *  boxlen_m             = (float)(boxlen * multiplier)   (dibr.py:36-37)
+ *  mode                 DIBR_B200_RASTER | DIBR_B200_SOFT_MASK
+ *  face_idx             (B,H,W) i64: output if RASTER, else INPUT (dibr_soft_mask alone)
+ *  interpolated_features(B,H,W,D) f32, output_weights (B,H,W,3) f32: outputs if RASTER
+ *  soft_mask            (B,H,W) f32: output if SOFT_MASK
+ * The workspace keeps the face bins; pass it unchanged to dibr_b200_backward
+ * with bins_valid = 1 to skip rebuilding them.
+ */
+int dibr_b200_forward(
+    int batch, int num_faces, int height, int width, int feat_dim,
+    const float* face_vertices_z, const float* face_vertices_image,
+    const float* face_features, const float* face_normals_z, const uint8_t* valid_faces,
+    float multiplier, float eps, int mode, float sigmainv, float boxlen_m, int knum,
+    float* interpolated_features, int64_t* face_idx, float* output_weights, float* soft_mask,
+    void* workspace, size_t workspace_bytes, dibr_b200_stream_t stream);
+
+/*
+ * Fused backward: grad wrt face_vertices_image (sum of the rasterize and the
+ * soft-mask branches, as autograd would add them) and wrt face_features.
+ * Replaces rasterization.py:355-371 + dibr.py:58-73 and the kernels behind them.
+ *  grad_features  (B,H,W,D) f32 or NULL (skips the rasterize branch; grad_face_features is zeroed)
+ *  grad_soft_mask (B,H,W)   f32 or NULL (skips the soft-mask branch)
+ *  soft_mask      forward's output (needed only with grad_soft_mask)
+ *  bins_valid     1: workspace still holds forward's bins for the same inputs
+ */
+int dibr_b200_backward(
+    int batch, int num_faces, int height, int width, int feat_dim,
+    const float* grad_features, const float* grad_soft_mask,
+    const int64_t* face_idx, const float* output_weights, const float* soft_mask,
+    const float* face_vertices_image, const float* face_features,
+    float multiplier, float eps, float sigmainv, float boxlen_m, int knum,
+    float* grad_face_vertices_image, float* grad_face_features,
+    void* workspace, size_t workspace_bytes, int bins_valid, dibr_b200_stream_t stream);
+
+/*
+ * Operator: kaolin::packed_rasterize_forward_cuda
+ * (kaolin/csrc/render/mesh/rasterization.h:23-32, rasterization.cpp:49-104).
+ * Packed valid faces of all meshes; coordinates already multiplied; tight bboxes
+ * [xmin,ymin,xmax,ymax]; first_idx_face_per_mesh is a DEVICE int64 array (B+1).
+ * selected_face_idx is relative to the mesh's first face, -1 = background.
+ */
+int dibr_b200_packed_rasterize_forward(
+    int batch, int64_t total_faces, int height, int width, int feat_dim,
+    const float* face_vertices_z, const float* face_vertices_image,
+    const float* face_bboxes, const float* face_features,
+    const int64_t* first_idx_face_per_mesh, float multiplier, float eps,
+    float* interpolated_features, int64_t* selected_face_idx, float* output_weights,
+    void* workspace, size_t workspace_bytes, dibr_b200_stream_t stream);
+
+/*
+ * Operator: kaolin::rasterize_backward_cuda
+ * (rasterization.h:34-41, rasterization.cpp:106-168).  face_vertices_image is the
+ * UNSCALED (B,F,3,2) tensor; selected_face_idx holds original face ids.
+ * (The reference's `interpolated_features` argument is never read by its kernel
+ * and is therefore not part of this ABI.)
+ */
+int dibr_b200_rasterize_backward(
+    int batch, int num_faces, int height, int width, int feat_dim,
+    const float* grad_interpolated_features, const int64_t* selected_face_idx,
+    const float* output_weights, const float* face_vertices_image,
+    const float* face_features, float eps,
+    float* grad_face_vertices_image, float* grad_face_features,
+    dibr_b200_stream_t stream);
+
+/*
+ * Operator: kaolin::dibr_soft_mask_forward_cuda
+ * (kaolin/csrc/render/mesh/dibr_soft_mask.h:23-30, dibr_soft_mask.cpp:48-108).
+ * face_vertices_image already multiplied; face_large_bboxes (B,F,4).
+ * close_face_prob (B,H,W,K) f32, close_face_idx (B,H,W,K) i64 (-1 padded),
+ * close_face_dist_type (B,H,W,K) u8 (0 padded; 1-3 edge, 4-6 vertex).
+ */
+int dibr_b200_soft_mask_forward(
+    int batch, int num_faces, int height, int width, int knum,
+    const float* face_vertices_image, const float* face_large_bboxes,
+    const int64_t* selected_face_idx, float sigmainv, float multiplier,
+    float* soft_mask, float* close_face_prob, int64_t* close_face_idx,
+    uint8_t* close_face_dist_type,
+    void* workspace, size_t workspace_bytes, dibr_b200_stream_t stream);
+
+/*
+ * Operator: kaolin::dibr_soft_mask_backward_cuda
+ * (dibr_soft_mask.h:32-42, dibr_soft_mask.cpp:110-183).
+ */
+int dibr_b200_soft_mask_backward(
+    int batch, int num_faces, int height, int width, int knum,
+    const float* grad_soft_mask, const float* soft_mask, const int64_t* selected_face_idx,
+    const float* close_face_prob, const int64_t* close_face_idx,
+    const uint8_t* close_face_dist_type, const float* face_vertices_image,
+    float sigmainv, float multiplier, float* grad_face_vertices_image,
+    dibr_b200_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIBR_B200_H_ */

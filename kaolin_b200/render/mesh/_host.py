@@ -1,0 +1,96 @@
+"""Host-side plumbing shared by the autograd wrappers: argument checks in the
+style of the reference's C++ wrappers (rasterization.cpp:70-85,
+dibr_soft_mask.cpp:63-82), workspace allocation, and the ctypes calls."""
+import ctypes
+
+import torch
+
+from ... import _lib
+
+
+def ptr(t):
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def check_tensors(func, named, dtype=torch.float32):
+    """All tensors on the same CUDA device with the expected dtype (no CPU path)."""
+    dev = None
+    for name, t in named:
+        if t is None:
+            continue
+        if not isinstance(t, torch.Tensor):
+            raise TypeError(f"{func}: {name} must be a torch.Tensor")
+        if not t.is_cuda:
+            raise RuntimeError(f"{func}: expected {name} to be a CUDA tensor "
+                               "(kaolin_b200 has no CPU path)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise RuntimeError(f"{func}: expected all tensors on {dev}, {name} is on {t.device}")
+        if dtype is not None and t.is_floating_point() and t.dtype != dtype:
+            raise RuntimeError(f"\"{func}\" not implemented for '{str(t.dtype).replace('torch.', '')}' "
+                               "(kaolin_b200 supports float32)")
+    return dev
+
+
+def check_size(func, name, t, shape):
+    if tuple(t.shape) != tuple(shape):
+        raise RuntimeError(f"{func}: expected {name} of size {list(shape)}, got {list(t.shape)}")
+
+
+def workspace(batch, total_faces, height, width, device):
+    n = _lib.lib().dibr_b200_workspace_bytes(batch, total_faces, height, width)
+    if n == 0:
+        raise RuntimeError("kaolin_b200: unsupported problem size "
+                           f"(batch={batch}, faces={total_faces}, image={height}x{width})")
+    return torch.empty(n, dtype=torch.uint8, device=device)
+
+
+def forward(mode, height, width, fvz, fvi, ff, fnz, valid_u8, multiplier, eps,
+            sigmainv, boxlen_m, knum, face_idx_in=None):
+    """Calls dibr_b200_forward; returns (feat, face_idx, weights, soft, workspace)."""
+    dev = fvi.device
+    B, F = fvi.shape[0], fvi.shape[1]
+    D = 0 if ff is None else ff.shape[-1]
+    raster = bool(mode & _lib.RASTER)
+    soft_on = bool(mode & _lib.SOFT_MASK)
+    feat = torch.empty((B, height, width, D), dtype=torch.float32, device=dev) if raster else None
+    wts = torch.empty((B, height, width, 3), dtype=torch.float32, device=dev) if raster else None
+    idx = torch.empty((B, height, width), dtype=torch.int64, device=dev) if raster else face_idx_in
+    soft = torch.empty((B, height, width), dtype=torch.float32, device=dev) if soft_on else None
+    ws = workspace(B, B * F, height, width, dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().dibr_b200_forward(
+            B, F, height, width, D, ptr(fvz), ptr(fvi), ptr(ff), ptr(fnz), ptr(valid_u8),
+            float(multiplier), float(eps), mode, float(sigmainv), float(boxlen_m), int(knum),
+            ptr(feat), ptr(idx), ptr(wts), ptr(soft), ptr(ws), ws.numel(), stream_ptr(dev))
+    _lib.check(st, "dibr_b200_forward")
+    return feat, idx, wts, soft, ws
+
+
+def backward(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps,
+             sigmainv, boxlen_m, knum, ws, bins_valid):
+    dev = fvi.device
+    B, F = fvi.shape[0], fvi.shape[1]
+    D = 0 if ff is None else ff.shape[-1]
+    g_fvi = torch.empty_like(fvi)
+    g_ff = torch.empty_like(ff) if ff is not None else None
+    if g_soft is None:
+        ws, ws_bytes, bins_valid = None, 0, False   # the rasterize branch needs no scratch
+    else:
+        if ws is None:
+            ws = workspace(B, B * F, height, width, dev)
+            bins_valid = False
+        ws_bytes = ws.numel()
+    with torch.cuda.device(dev):
+        st = _lib.lib().dibr_b200_backward(
+            B, F, height, width, D, ptr(g_feat), ptr(g_soft), ptr(face_idx), ptr(wts), ptr(soft),
+            ptr(fvi), ptr(ff), float(multiplier), float(eps), float(sigmainv), float(boxlen_m),
+            int(knum), ptr(g_fvi), ptr(g_ff), ptr(ws), ws_bytes, int(bool(bins_valid)),
+            stream_ptr(dev))
+    _lib.check(st, "dibr_b200_backward")
+    return g_fvi, g_ff

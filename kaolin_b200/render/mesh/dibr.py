@@ -1,0 +1,124 @@
+"""``dibr_soft_mask`` / ``dibr_rasterization`` — drop-in for kaolin/render/mesh/dibr.py.
+
+``dibr_rasterization`` is ONE autograd node: the forward is a single fused tile
+kernel (rasterize + soft mask share the face binning), the backward adds the
+rasterize and soft-mask gradients of ``face_vertices_image`` in place of the
+reference's two nodes + autograd sum.  Results are identical to
+calling ``rasterize`` then ``dibr_soft_mask`` (tests/test_api_gpu.py).
+"""
+import torch
+from torch.autograd import Function
+
+from ... import _lib
+from . import _host
+from .rasterization import _check_inputs
+
+__all__ = ["dibr_soft_mask", "dibr_rasterization"]
+
+
+class DibrSoftMaskB200(Function):
+    """Counterpart of ``DibrSoftMaskCuda`` (dibr.py:27-73).  The K-lists the
+    reference saves (13*knum bytes per pixel) are recomputed in backward."""
+
+    @staticmethod
+    def forward(ctx, face_vertices_image, selected_face_idx, sigmainv, boxlen, knum, multiplier):
+        fvi = face_vertices_image.contiguous()
+        idx = selected_face_idx.contiguous()
+        B, H, W = idx.shape
+        boxlen_m = boxlen * multiplier
+        _, _, _, soft, ws = _host.forward(_lib.SOFT_MASK, H, W, None, fvi, None, None, None,
+                                          multiplier, 0., sigmainv, boxlen_m, knum, face_idx_in=idx)
+        ctx.save_for_backward(soft, fvi, idx)
+        ctx.params = (sigmainv, boxlen_m, knum, multiplier)
+        ctx.ws = ws
+        return soft
+
+    @staticmethod
+    def backward(ctx, grad_soft_mask):
+        soft, fvi, idx = ctx.saved_tensors
+        sigmainv, boxlen_m, knum, multiplier = ctx.params
+        B, H, W = idx.shape
+        g_fvi, _ = _host.backward(H, W, None, grad_soft_mask.contiguous(), idx, None, soft, fvi, None,
+                                  multiplier, 0., sigmainv, boxlen_m, knum, ctx.ws, True)
+        return g_fvi, None, None, None, None, None
+
+
+def dibr_soft_mask(face_vertices_image, selected_face_idx, sigmainv=7000, boxlen=0.02,
+                   knum=30, multiplier=1000.):
+    r"""Soft mask of DIB-R (see kaolin.render.mesh.dibr_soft_mask, dibr.py:75-117)."""
+    _host.check_tensors("dibr_soft_mask", [("face_vertices_image", face_vertices_image),
+                                           ("selected_face_idx", selected_face_idx)])
+    if face_vertices_image.dim() != 4 or tuple(face_vertices_image.shape[2:]) != (3, 2):
+        raise RuntimeError("dibr_soft_mask: face_vertices_image must be of shape "
+                           "(batch_size, num_faces, 3, 2)")
+    if selected_face_idx.dtype != torch.int64 or selected_face_idx.dim() != 3 \
+            or selected_face_idx.shape[0] != face_vertices_image.shape[0]:
+        raise RuntimeError("dibr_soft_mask: selected_face_idx must be a LongTensor of shape "
+                           "(batch_size, height, width)")
+    return DibrSoftMaskB200.apply(face_vertices_image, selected_face_idx, sigmainv, boxlen,
+                                  knum, multiplier)
+
+
+class DibrRasterizationB200(Function):
+    """rasterize(valid = face_normals_z >= 0) + dibr_soft_mask in one node."""
+
+    @staticmethod
+    def forward(ctx, height, width, face_vertices_z, face_vertices_image, face_features,
+                face_normals_z, sigmainv, boxlen, knum, multiplier, eps, soft_multiplier):
+        fvz = face_vertices_z.contiguous()
+        fvi = face_vertices_image.contiguous()
+        ff = face_features.contiguous()
+        fnz = face_normals_z.contiguous()
+        boxlen_m = boxlen * soft_multiplier
+        feat, face_idx, wts, soft, ws = _host.forward(
+            _lib.RASTER | _lib.SOFT_MASK, height, width, fvz, fvi, ff, fnz, None,
+            multiplier, eps, sigmainv, boxlen_m, knum)
+        ctx.save_for_backward(face_idx, wts, soft, fvi, ff)
+        ctx.mark_non_differentiable(face_idx)
+        ctx.params = (height, width, multiplier, eps, sigmainv, boxlen_m, knum)
+        ctx.ws = ws
+        return feat, soft, face_idx
+
+    @staticmethod
+    def backward(ctx, grad_features, grad_soft_mask, grad_face_idx):
+        face_idx, wts, soft, fvi, ff = ctx.saved_tensors
+        height, width, multiplier, eps, sigmainv, boxlen_m, knum = ctx.params
+        g_feat = None if grad_features is None else grad_features.contiguous()
+        g_soft = None if grad_soft_mask is None else grad_soft_mask.contiguous()
+        g_fvi, g_ff = _host.backward(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff,
+                                     multiplier, eps, sigmainv, boxlen_m, knum, ctx.ws, True)
+        return None, None, None, g_fvi, g_ff, None, None, None, None, None, None, None
+
+
+def dibr_rasterization(height, width, face_vertices_z, face_vertices_image, face_features,
+                       face_normals_z, sigmainv=7000, boxlen=0.02, knum=30, multiplier=None,
+                       eps=None, rast_backend='cuda'):
+    r"""Fully differentiable DIB-R renderer (see kaolin.render.mesh.dibr_rasterization,
+    dibr.py:119-209): returns (interpolated_features | tuple, soft_mask, face_idx)."""
+    if rast_backend != 'cuda':
+        raise ValueError(f'"{rast_backend}" is not a valid backend, '
+                         'kaolin_b200 only provides ["cuda"]')
+    if multiplier is None:
+        multiplier = 1000
+        soft_multiplier = 1000.          # dibr.py:200
+    else:
+        soft_multiplier = multiplier
+    if eps is None:
+        eps = 1e-8
+    _face_features = torch.cat(face_features, dim=-1) \
+        if isinstance(face_features, (list, tuple)) else face_features
+    B, F = _check_inputs("dibr_rasterization", face_vertices_z, face_vertices_image, _face_features)
+    _host.check_tensors("dibr_rasterization", [("face_vertices_z", face_vertices_z),
+                                               ("face_normals_z", face_normals_z)])
+    _host.check_size("dibr_rasterization", "face_normals_z", face_normals_z, (B, F))
+    image_features, soft_mask, face_idx = DibrRasterizationB200.apply(
+        height, width, face_vertices_z, face_vertices_image, _face_features, face_normals_z,
+        sigmainv, boxlen, knum, multiplier, eps, soft_multiplier)
+    if isinstance(face_features, (list, tuple)):
+        _image_features = []
+        cur_idx = 0
+        for face_feature in face_features:
+            _image_features.append(image_features[..., cur_idx:cur_idx + face_feature.shape[-1]])
+            cur_idx += face_feature.shape[-1]
+        image_features = tuple(_image_features)
+    return image_features, soft_mask, face_idx

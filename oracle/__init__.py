@@ -281,3 +281,92 @@ def dibr_rasterization_backward(grad_features, grad_soft_mask, face_idx, output_
     gxy_s = dibr_soft_mask_backward(grad_soft_mask, face_vertices_image, face_idx,
                                     sigmainv, boxlen, knum, _m)
     return gxy_r.astype(np.float64) + gxy_s.astype(np.float64), gff, gxy_r, gxy_s
+
+
+# --------------------------------------------------------------------------
+# bounded-sample driver for bench.py's cpu_baseline / --impl reference legs
+# --------------------------------------------------------------------------
+class RowSample:
+    """DIB-R forward+backward of image rows [row0,row1) of every view on the CPU.
+
+    The host-side preparation (packing, bboxes) is done once in __init__ (the
+    reference does it with a dozen torch kernels per call; it is negligible next
+    to the brute-force pixel loops), ``run()`` executes the four restated
+    kernels on the strip with the OpenMP threads set by ``set_threads``.
+    """
+
+    def __init__(self, height, width, fvz, fvi, ff, fnz, g_feat, g_soft, row0, row1,
+                 sigmainv=7000, boxlen=0.02, knum=30, multiplier=1000., eps=1e-8, strips=None):
+        self.H, self.W, self.row0, self.row1 = height, width, int(row0), int(row1)
+        # strips: list of (row0,row1) blocks; default one block [row0,row1)
+        self.strips = [(int(a), int(b)) for a, b in strips] if strips else [(int(row0), int(row1))]
+        self.m, self.eps, self.sigmainv, self.K = float(multiplier), float(eps), float(sigmainv), int(knum)
+        fvz, fvi, ff = _f32(fvz), _f32(fvi), _f32(ff)
+        B, F = fvz.shape[:2]
+        D = ff.shape[-1]
+        self.B, self.F, self.D = B, F, D
+        vf = np.asarray(fnz) >= 0.
+        b_idx, f_idx = np.nonzero(vf)
+        self.f_idx = f_idx
+        self.first = np.zeros(B + 1, np.int64)
+        np.cumsum(vf.sum(1), out=self.first[1:])
+        self.p_xy = np.ascontiguousarray(fvi[b_idx, f_idx] * np.float32(multiplier))
+        self.p_z = np.ascontiguousarray(fvz[b_idx, f_idx])
+        self.p_ff = np.ascontiguousarray(ff[b_idx, f_idx])
+        self.p_bb = np.ascontiguousarray(np.concatenate([self.p_xy.min(1), self.p_xy.max(1)], 1))
+        self.fvi, self.ff = fvi, ff
+        self.fvi_m = np.ascontiguousarray(fvi * np.float32(multiplier))
+        self.bb_large = np.ascontiguousarray(_large_bboxes(self.fvi_m, boxlen, multiplier))
+        self.g_feat, self.g_soft = _f32(g_feat), _f32(g_soft)
+        P = (B, height, width)
+        self.sel = np.full(P, -1, np.int64)
+        self.idx = np.full(P, -1, np.int64)
+        self.w = np.zeros(P + (3,), np.float32)
+        self.out = np.zeros(P + (D,), np.float32)
+        self.soft = np.zeros(P, np.float32)
+        self.prob = np.zeros(P + (knum,), np.float32)
+        self.cidx = np.full(P + (knum,), -1, np.int64)
+        self.ctype = np.zeros(P + (knum,), np.uint8)
+        self.gxy = np.zeros_like(fvi)
+        self.gxy2 = np.zeros_like(fvi)
+        self.gff = np.zeros_like(ff)
+
+    @property
+    def pixels(self):
+        return self.B * sum(b - a for a, b in self.strips) * self.W
+
+    def run(self):
+        for a, b in self.strips:
+            self.row0, self.row1 = a, b
+            out = self._run_strip()
+        return out
+
+    def _run_strip(self):
+        L = lib()
+        c_i, c_f = ctypes.c_int, ctypes.c_float
+        B, H, W, F, D, K = self.B, self.H, self.W, self.F, self.D, self.K
+        r0, r1 = c_i(self.row0), c_i(self.row1)
+        L.oracle_rasterize_forward_rows(
+            c_i(B), c_i(H), c_i(W), c_i(D), _p(self.p_z, _f32p), _p(self.p_xy, _f32p),
+            _p(self.p_bb, _f32p), _p(self.p_ff, _f32p), _p(self.first, _i64p), c_f(self.m),
+            c_f(self.eps), _p(self.sel, _i64p), _p(self.w, _f32p), _p(self.out, _f32p), r0, r1)
+        rows = slice(self.row0, self.row1)
+        sel = self.sel[:, rows]
+        cov = sel >= 0
+        packed = sel + self.first[:-1].reshape(-1, 1, 1)
+        idx = np.full(sel.shape, -1, np.int64)
+        idx[cov] = self.f_idx[packed[cov]]
+        self.idx[:, rows] = idx
+        L.oracle_soft_mask_forward_rows(
+            c_i(B), c_i(H), c_i(W), c_i(F), c_i(K), _p(self.fvi_m, _f32p), _p(self.bb_large, _f32p),
+            _p(self.idx, _i64p), c_f(self.sigmainv), c_f(self.m), _p(self.soft, _f32p),
+            _p(self.prob, _f32p), _p(self.cidx, _i64p), _p(self.ctype, _u8p), r0, r1)
+        L.oracle_rasterize_backward_rows(
+            c_i(B), c_i(H), c_i(W), c_i(F), c_i(D), _p(self.g_feat, _f32p), _p(self.idx, _i64p),
+            _p(self.w, _f32p), _p(self.fvi, _f32p), _p(self.ff, _f32p), c_f(self.eps),
+            _p(self.gxy, _f32p), _p(self.gff, _f32p), r0, r1)
+        L.oracle_soft_mask_backward_rows(
+            c_i(B), c_i(H), c_i(W), c_i(F), c_i(K), _p(self.g_soft, _f32p), _p(self.soft, _f32p),
+            _p(self.idx, _i64p), _p(self.prob, _f32p), _p(self.cidx, _i64p), _p(self.ctype, _u8p),
+            _p(self.fvi_m, _f32p), c_f(self.sigmainv), c_f(self.m), _p(self.gxy2, _f32p), r0, r1)
+        return self.gxy, self.gxy2, self.gff

@@ -54,7 +54,7 @@ static inline float pix_y(float multiplier, int height, int iy) {
  * Outputs are fully written (the host wrapper's at::full(-1)/at::zeros,
  * rasterization.cpp:88-93, are folded in).
  */
-void oracle_rasterize_forward(
+void oracle_rasterize_forward_rows(
     int batch_size, int height, int width, int num_features,
     const float* face_vertices_z,      /* (NF,3)   */
     const float* face_vertices_image,  /* (NF,3,2) */
@@ -64,14 +64,15 @@ void oracle_rasterize_forward(
     float multiplier, float eps,
     int64_t* selected_face_idx,        /* (B,H,W)   */
     float* output_weights,             /* (B,H,W,3) */
-    float* interpolated_features)      /* (B,H,W,D) */
+    float* interpolated_features,      /* (B,H,W,D) */
+    int row0, int row1)                /* only image rows [row0,row1) are computed/written */
 {
   const int D = num_features;
   for (int bidx = 0; bidx < batch_size; bidx++) {
     const int first_id_faces = (int)first_idx_face_per_mesh[bidx];
     const int last_id_faces = (int)first_idx_face_per_mesh[bidx + 1];
 #pragma omp parallel for schedule(dynamic, 64)
-    for (int pixel_idx = 0; pixel_idx < height * width; pixel_idx++) {
+    for (int pixel_idx = row0 * width; pixel_idx < row1 * width; pixel_idx++) {
       const int wididx = pixel_idx % width;
       const int heiidx = (pixel_idx - wididx) / width;
       float max_z0 = -INFINITY;
@@ -129,12 +130,25 @@ void oracle_rasterize_forward(
   }
 }
 
+void oracle_rasterize_forward(
+    int batch_size, int height, int width, int num_features,
+    const float* face_vertices_z, const float* face_vertices_image, const float* face_bboxes,
+    const float* face_features, const int64_t* first_idx_face_per_mesh,
+    float multiplier, float eps,
+    int64_t* selected_face_idx, float* output_weights, float* interpolated_features)
+{
+  oracle_rasterize_forward_rows(batch_size, height, width, num_features, face_vertices_z,
+                                face_vertices_image, face_bboxes, face_features,
+                                first_idx_face_per_mesh, multiplier, eps, selected_face_idx,
+                                output_weights, interpolated_features, 0, height);
+}
+
 /*
  * rasterization_cuda.cu:238-402.  face_vertices_image is UNSCALED here
  * (rasterization.py:347-350 saves the original tensor).  Accumulation in
  * double (see header).  Outputs (B,F,3,2) and (B,F,3,D), fully written.
  */
-void oracle_rasterize_backward(
+void oracle_rasterize_backward_rows(
     int batch_size, int height, int width, int num_faces, int feat_dim,
     const float* grad_interpolated_features, /* (B,H,W,D) */
     const int64_t* selected_face_idx,        /* (B,H,W), original face ids */
@@ -143,7 +157,8 @@ void oracle_rasterize_backward(
     const float* face_features,              /* (B,F,3,D) */
     float eps,
     float* grad_face_vertices_image,         /* (B,F,3,2) */
-    float* grad_face_features)               /* (B,F,3,D) */
+    float* grad_face_features,               /* (B,F,3,D) */
+    int row0, int row1)                      /* only pixels of rows [row0,row1) contribute */
 {
   const int D = feat_dim;
   const int64_t n_xy = (int64_t)batch_size * num_faces * 6;
@@ -154,6 +169,8 @@ void oracle_rasterize_backward(
 #pragma omp parallel for schedule(dynamic, 256)
   for (int64_t true_pixel_idx = 0; true_pixel_idx < batch_size * num_pixels; true_pixel_idx++) {
     const int64_t batch_idx = true_pixel_idx / num_pixels;
+    const int row = (int)((true_pixel_idx % num_pixels) / width);
+    if (row < row0 || row >= row1) continue;
     const int face_idx = (int)selected_face_idx[true_pixel_idx];
     if (face_idx < 0) continue;
     const float* g = grad_interpolated_features + true_pixel_idx * D;
@@ -233,6 +250,18 @@ void oracle_rasterize_backward(
   free(acc_ff);
 }
 
+void oracle_rasterize_backward(
+    int batch_size, int height, int width, int num_faces, int feat_dim,
+    const float* grad_interpolated_features, const int64_t* selected_face_idx,
+    const float* output_weights, const float* face_vertices_image, const float* face_features,
+    float eps, float* grad_face_vertices_image, float* grad_face_features)
+{
+  oracle_rasterize_backward_rows(batch_size, height, width, num_faces, feat_dim,
+                                 grad_interpolated_features, selected_face_idx, output_weights,
+                                 face_vertices_image, face_features, eps, grad_face_vertices_image,
+                                 grad_face_features, 0, height);
+}
+
 /*
  * dibr_soft_mask_cuda.cu:27-184.  face_vertices_image is already multiplied
  * (dibr.py:32), face_large_bboxes = [min - boxlen*m, max + boxlen*m]
@@ -240,7 +269,7 @@ void oracle_rasterize_backward(
  * fully written (padding -1 / 0 / 0 as dibr_soft_mask.cpp:86-97 allocates).
  * Any of close_face_prob / close_face_idx / close_face_dist_type may be NULL.
  */
-void oracle_soft_mask_forward(
+void oracle_soft_mask_forward_rows(
     int batch_size, int height, int width, int num_faces, int knum,
     const float* face_vertices_image,  /* (B,F,3,2) * multiplier */
     const float* face_bboxes,          /* (B,F,4) enlarged */
@@ -249,13 +278,15 @@ void oracle_soft_mask_forward(
     float* soft_mask,                  /* (B,H,W)   */
     float* close_face_prob,            /* (B,H,W,K) or NULL */
     int64_t* close_face_idx,           /* (B,H,W,K) or NULL */
-    uint8_t* close_face_dist_type)     /* (B,H,W,K) or NULL */
+    uint8_t* close_face_dist_type,     /* (B,H,W,K) or NULL */
+    int row0, int row1)                /* only image rows [row0,row1) are computed/written */
 {
   const int64_t P = (int64_t)batch_size * height * width;
 #pragma omp parallel for schedule(dynamic, 64)
   for (int64_t totalidx1 = 0; totalidx1 < P; totalidx1++) {
     const int wididx = (int)(totalidx1 % width);
     const int heiidx = (int)((totalidx1 / width) % height);
+    if (heiidx < row0 || heiidx >= row1) continue;
     const int bidx = (int)(totalidx1 / ((int64_t)width * height));
     const int64_t totalidxk = totalidx1 * knum;
     float probs_local[knum > 0 ? knum : 1];
@@ -320,11 +351,22 @@ void oracle_soft_mask_forward(
   }
 }
 
+void oracle_soft_mask_forward(
+    int batch_size, int height, int width, int num_faces, int knum,
+    const float* face_vertices_image, const float* face_bboxes, const int64_t* selected_face_idx,
+    float sigmainv, float multiplier, float* soft_mask, float* close_face_prob,
+    int64_t* close_face_idx, uint8_t* close_face_dist_type)
+{
+  oracle_soft_mask_forward_rows(batch_size, height, width, num_faces, knum, face_vertices_image,
+                                face_bboxes, selected_face_idx, sigmainv, multiplier, soft_mask,
+                                close_face_prob, close_face_idx, close_face_dist_type, 0, height);
+}
+
 /*
  * dibr_soft_mask_cuda.cu:230-353.  Per-term arithmetic as the reference
  * (float variables, double where the literals promote); accumulation in double.
  */
-void oracle_soft_mask_backward(
+void oracle_soft_mask_backward_rows(
     int batch_size, int height, int width, int num_faces, int knum,
     const float* grad_soft_mask,        /* (B,H,W) */
     const float* soft_mask,             /* (B,H,W) */
@@ -334,7 +376,8 @@ void oracle_soft_mask_backward(
     const uint8_t* close_face_dist_type,/* (B,H,W,K) */
     const float* face_vertices_image,   /* (B,F,3,2) * multiplier */
     float sigmainv, float multiplier,
-    float* grad_face_vertices_image)    /* (B,F,3,2) */
+    float* grad_face_vertices_image,    /* (B,F,3,2) */
+    int row0, int row1)                 /* only pixels of rows [row0,row1) contribute */
 {
   const int64_t n_xy = (int64_t)batch_size * num_faces * 6;
   double* acc = (double*)calloc((size_t)n_xy, sizeof(double));
@@ -345,6 +388,7 @@ void oracle_soft_mask_backward(
     const int heiidx = (int)((totalidx1 / width) % height);
     const int bidx = (int)(totalidx1 / ((int64_t)width * height));
     const int64_t totalidxk = totalidx1 * knum;
+    if (heiidx < row0 || heiidx >= row1) continue;
     if (selected_face_idx[totalidx1] >= 0) continue;
     const float x0 = pix_x(multiplier, width, wididx);
     const float y0 = pix_y(multiplier, height, heiidx);
@@ -396,6 +440,19 @@ void oracle_soft_mask_backward(
   }
   for (int64_t i = 0; i < n_xy; i++) grad_face_vertices_image[i] = (float)acc[i];
   free(acc);
+}
+
+void oracle_soft_mask_backward(
+    int batch_size, int height, int width, int num_faces, int knum,
+    const float* grad_soft_mask, const float* soft_mask, const int64_t* selected_face_idx,
+    const float* close_face_prob, const int64_t* close_face_idx,
+    const uint8_t* close_face_dist_type, const float* face_vertices_image,
+    float sigmainv, float multiplier, float* grad_face_vertices_image)
+{
+  oracle_soft_mask_backward_rows(batch_size, height, width, num_faces, knum, grad_soft_mask,
+                                 soft_mask, selected_face_idx, close_face_prob, close_face_idx,
+                                 close_face_dist_type, face_vertices_image, sigmainv, multiplier,
+                                 grad_face_vertices_image, 0, height);
 }
 
 /* Thread control for the cpu_baseline leg of bench.py. */

@@ -1,0 +1,377 @@
+"""Parity of the sm_100a kernels (through the C ABI / public API) with the oracle.
+
+Bars (BASELINE.json north_star): face_idx / close_face_idx / dist_type bit-exact;
+forward floats within 1e-5 (they are in fact produced by the same operation
+trees, so most are bit-equal); gradients within 1e-5 of the gradient's scale
+(max |err| <= 1e-5 * max |ref| — the reference itself is run-to-run
+non-deterministic at this level because it accumulates with float atomics).
+Where oracle/_ref (the reference's own CUDA kernels, compiled in place) is
+present, it is used as a second, independent oracle.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import oracle
+from oracle import ref_cuda
+from kaolin_b200 import synthetic
+from kaolin_b200 import _C as b200_C
+from kaolin_b200.render.mesh import rasterize, dibr_soft_mask, dibr_rasterization
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+GRAD_REL = 1e-5
+
+
+def T(a, grad=False):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t.requires_grad_(True) if grad else t
+
+
+def N(t):
+    return t.detach().cpu().numpy()
+
+
+def rel_err(a, ref):
+    return float(np.abs(a - ref).max() / max(np.abs(ref).max(), 1e-30))
+
+
+SCENES = {
+    "ico1_64": (lambda: synthetic.icosphere_views(1, 1, seed=1), 64, 64),          # BASELINE configs[0]
+    "ico3_96x80": (lambda: synthetic.icosphere_views(2, 3, seed=2), 96, 80),
+    "ico4_256": (lambda: synthetic.icosphere_views(2, 4, seed=3), 256, 256),       # configs[1] shape, B=2
+    "soup300_37x53": (lambda: synthetic.triangle_soup(2, 300, seed=3, coverage=3.0), 37, 53),
+    "soup_big_faces_130": (lambda: synthetic.triangle_soup(2, 60, seed=4, coverage=40.0), 130, 130),
+    "soup2000_200x72": (lambda: synthetic.triangle_soup(1, 2000, seed=5), 200, 72),
+}
+
+
+def _run_fused(fvz, fvi, fnz, ff, H, W, g_feat, g_soft, **kw):
+    t_fvi, t_ff = T(fvi, True), T(ff, True)
+    feat, soft, idx = dibr_rasterization(H, W, T(fvz), t_fvi, t_ff, T(fnz), **kw)
+    torch.autograd.backward([feat, soft], [T(g_feat), T(g_soft)])
+    return N(feat), N(soft), N(idx), N(t_fvi.grad), N(t_ff.grad)
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+def test_fused_dibr_vs_oracle(name):
+    gen, H, W = SCENES[name]
+    fvz, fvi, fnz = gen()
+    B, F = fvz.shape[:2]
+    D = 3
+    ff = synthetic.random_features(B, F, D, seed=11)
+    rng = np.random.default_rng(12)
+    g_feat = rng.uniform(size=(B, H, W, D)).astype(np.float32)
+    g_soft = rng.uniform(size=(B, H, W)).astype(np.float32)
+    feat, soft, idx, g_fvi, g_ff = _run_fused(fvz, fvi, fnz, ff, H, W, g_feat, g_soft)
+
+    o_feat, o_soft, o_idx, o_w = oracle.dibr_rasterization(H, W, fvz, fvi, ff, fnz, return_weights=True)
+    assert (o_idx >= 0).mean() > 0.01
+    assert np.array_equal(idx, o_idx)
+    np.testing.assert_allclose(feat, o_feat, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(soft, o_soft, rtol=0, atol=1e-5)
+    o_gxy, o_gff, o_gr, o_gs = oracle.dibr_rasterization_backward(g_feat, g_soft, o_idx, o_w, fvi, ff)
+    assert np.abs(o_gs).max() > 0 and np.abs(o_gr).max() > 0
+    assert rel_err(g_fvi, o_gxy) <= GRAD_REL, rel_err(g_fvi, o_gxy)
+    assert rel_err(g_ff, o_gff) <= GRAD_REL, rel_err(g_ff, o_gff)
+
+
+@pytest.mark.skipif(not ref_cuda.available(), reason="oracle/_ref (reference CUDA build) not present")
+@pytest.mark.parametrize("name", list(SCENES))
+def test_fused_dibr_vs_reference_cuda(name):
+    """The reference's own kernels on the same GPU: face_idx bit-exact, 1e-5 elsewhere."""
+    gen, H, W = SCENES[name]
+    fvz, fvi, fnz = gen()
+    B, F = fvz.shape[:2]
+    ff = synthetic.random_features(B, F, 3, seed=11)
+    rng = np.random.default_rng(12)
+    g_feat = rng.uniform(size=(B, H, W, 3)).astype(np.float32)
+    g_soft = rng.uniform(size=(B, H, W)).astype(np.float32)
+    feat, soft, idx, g_fvi, g_ff = _run_fused(fvz, fvi, fnz, ff, H, W, g_feat, g_soft)
+    r = ref_cuda.dibr_forward_backward(H, W, T(fvz), T(fvi), T(ff), T(fnz), T(g_feat), T(g_soft))
+    assert np.array_equal(idx, N(r["face_idx"]))
+    np.testing.assert_allclose(feat, N(r["features"]), rtol=0, atol=1e-5)
+    np.testing.assert_allclose(soft, N(r["soft_mask"]), rtol=0, atol=1e-5)
+    assert rel_err(g_fvi, N(r["grad_fvi"])) <= 3e-5     # both sides accumulate in fp32 atomics
+    assert rel_err(g_ff, N(r["grad_ff"])) <= 3e-5
+
+
+def test_composition_equals_separate_calls():
+    """test_dibr.py:482-529: dibr_rasterization == rasterize + dibr_soft_mask, torch.equal."""
+    fvz, fvi, fnz = synthetic.icosphere_views(3, 3, seed=7)
+    B, F = fvz.shape[:2]
+    uv = synthetic.random_features(B, F, 2, seed=1)
+    ones = np.ones((B, F, 3, 1), np.float32)
+    H, W = 70, 90
+    for kw in ({}, {"sigmainv": 70, "boxlen": 0.2, "knum": 20, "multiplier": 100, "eps": 1e-7}):
+        (a_uv, a_m), a_soft, a_idx = dibr_rasterization(H, W, T(fvz), T(fvi), [T(uv), T(ones)], T(fnz), **kw)
+        rkw = {k: kw[k] for k in ("multiplier", "eps") if k in kw}
+        (b_uv, b_m), b_idx = rasterize(H, W, T(fvz), T(fvi), [T(uv), T(ones)], T(fnz) >= 0., **rkw)
+        skw = {k: kw[k] for k in ("sigmainv", "boxlen", "knum") if k in kw}
+        b_soft = dibr_soft_mask(T(fvi), b_idx, multiplier=kw.get("multiplier", 1000.), **skw)
+        assert torch.equal(a_idx, b_idx)
+        assert torch.equal(a_uv, b_uv) and torch.equal(a_m, b_m)
+        assert torch.equal(a_soft, b_soft)
+        assert a_idx.dtype == torch.int64 and a_uv.shape == (B, H, W, 2) and a_m.shape == (B, H, W, 1)
+
+
+@pytest.mark.parametrize("with_valid", [False, True])
+def test_rasterize_api_vs_naive_golden(golden_dir, with_valid):
+    """test_rasterization.py:137-289 against the stored outputs of the reference's naive oracle."""
+    g = np.load(os.path.join(golden_dir, "rasterize_model.npz"))
+    tag = "valid" if with_valid else "all"
+    fvi, fvz, uvs = g["fvi"], g["fvz"], g["face_uvs"]
+    kwargs = {"valid_faces": T(g["valid_faces"])} if with_valid else {}
+    t_fvz, t_fvi, t_uv = T(fvz, True), T(fvi, True), T(uvs, True)
+    t_ones = T(np.ones_like(uvs[..., :1]), True)
+    (uv_map, mask), face_idx = rasterize(32, 32, t_fvz, t_fvi, [t_uv, t_ones], backend="cuda", **kwargs)
+    assert torch.equal(face_idx.cpu(), torch.from_numpy(g[tag + "_face_idx"].astype(np.int64)))
+    feats = torch.cat([uv_map, mask], -1)
+    np.testing.assert_allclose(N(feats), g[tag + "_features"], rtol=1e-5, atol=1e-5)
+    feats.backward(T(g["grad_out"]))
+    assert t_fvz.grad is None or torch.all(t_fvz.grad == 0.)          # test_rasterization.py:227
+    np.testing.assert_allclose(N(t_fvi.grad), g[tag + "_grad_fvi"], rtol=1e-3, atol=1e-2)
+    np.testing.assert_allclose(N(t_uv.grad), g[tag + "_grad_uvs"], rtol=1e-3, atol=1e-3)
+    np.testing.assert_allclose(N(t_ones.grad), g[tag + "_grad_ones"], rtol=1e-3, atol=1e-3)
+    assert rel_err(N(t_fvi.grad), g[tag + "_grad_fvi"]) <= 1e-4
+
+
+def _mask_iou(soft, face_idx):
+    """kaolin/metrics/render.py:18-41 with the shifted target of test_dibr.py:182-186."""
+    mask = face_idx != -1
+    shifted = torch.nn.functional.pad(mask, (0, 5))[..., 5:]
+    B = soft.shape[0]
+    mul = soft * shifted
+    add = soft + shifted
+    up = torch.sum(mul.reshape(B, -1), dim=1)
+    down = torch.sum((add - mul).reshape(B, -1), dim=1)
+    return 1.0 - torch.mean(up / (down + 1e-10))
+
+
+@pytest.mark.parametrize("sigmainv", [7000, 70])
+@pytest.mark.parametrize("boxlen", [0.02, 0.2])
+@pytest.mark.parametrize("multiplier", [1000, 100, 1])
+@pytest.mark.parametrize("knum", [30, 20])
+def test_simple_scene_golden(golden_dir, sigmainv, boxlen, multiplier, knum):
+    """test_dibr.py:109-191 (TestSimpleDibrSoftMask) at the `_C` operator and API level."""
+    g = np.load(os.path.join(golden_dir, "dibr_simple.npz"))
+    key = f"s{sigmainv}_b{boxlen}_"
+    H, W = 35, 31
+    fvi, fvz = T(g["fvi"]), T(g["fvz"])
+    ff = torch.zeros(fvz.shape + (1,), device=DEV)
+    _, face_idx = rasterize(H, W, fvz, fvi, ff)
+    assert torch.equal(face_idx.cpu(), torch.from_numpy(g["face_idx"].astype(np.int64)))
+    fvi_m = fvi * multiplier
+    pmin = torch.min(fvi_m, dim=-2)[0]
+    pmax = torch.max(fvi_m, dim=-2)[0]
+    bb = torch.cat([pmin - boxlen * multiplier, pmax + boxlen * multiplier], dim=-1)
+    soft, prob, cidx, ctype = b200_C.render.mesh.dibr_soft_mask_forward_cuda(
+        fvi_m, bb, face_idx, sigmainv, knum, multiplier)
+    gt_soft = torch.from_numpy(g[key + "soft_mask"]).to(DEV)
+    assert torch.allclose(soft, gt_soft, atol=1e-5, rtol=1e-5)
+    assert torch.equal(cidx.cpu(), torch.from_numpy(g[key + "close_face_idx"][..., :knum].astype(np.int64)))
+    assert torch.allclose(prob.cpu(), torch.from_numpy(g[key + "close_face_prob"][..., :knum]),
+                          atol=1e-5, rtol=1e-5)
+    assert torch.equal(ctype.cpu(), torch.from_numpy(g[key + "close_face_dist_type"][..., :knum]))
+    # Python API forward + backward (test_dibr.py:142-191)
+    t_fvi = fvi.detach().clone().requires_grad_(True)
+    soft2 = dibr_soft_mask(t_fvi, face_idx, sigmainv, boxlen, knum, multiplier)
+    assert torch.allclose(soft2, gt_soft, atol=1e-5, rtol=1e-5)
+    _mask_iou(soft2, face_idx).backward()
+    gt_grad = torch.from_numpy(g[key + "grad_fvi"]).to(DEV)
+    assert torch.allclose(t_fvi.grad, gt_grad, rtol=1e-5, atol=1e-5)
+    # operator-level backward from the stored K-lists
+    s_req = soft.clone().requires_grad_(True)
+    _mask_iou(s_req, face_idx).backward()
+    g_op = b200_C.render.mesh.dibr_soft_mask_backward_cuda(
+        s_req.grad.contiguous(), soft, face_idx, prob, cidx, ctype, fvi_m, sigmainv, multiplier)
+    assert torch.allclose(g_op, gt_grad, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("sigmainv,boxlen", [(7000, 0.02), (70, 0.01)])
+@pytest.mark.parametrize("knum", [30, 40])
+@pytest.mark.parametrize("flip", [False, True])
+def test_sphere_scene_golden(golden_dir, sigmainv, boxlen, knum, flip):
+    """test_dibr.py:309-394 (TestDibrSoftMask) at the `_C` operator and API level."""
+    g = np.load(os.path.join(golden_dir, "dibr_sphere.npz"))
+    key = f"s{sigmainv}_b{boxlen}_"
+    H, W = 35, 31
+    fvi_np, fvz_np = g["fvi"], g["fvz"]
+    if flip:
+        fvi_np, fvz_np = fvi_np[:, :, ::-1], fvz_np[:, :, ::-1]
+    fvi, fvz = T(fvi_np), T(fvz_np)
+    ff = torch.zeros(fvz.shape + (1,), device=DEV)
+    _, face_idx = rasterize(H, W, fvz, fvi, ff)
+    for multiplier in (1000, 100):
+        fvi_m = fvi * multiplier
+        pmin = torch.min(fvi_m, dim=-2)[0]
+        pmax = torch.max(fvi_m, dim=-2)[0]
+        bb = torch.cat([pmin - boxlen * multiplier, pmax + boxlen * multiplier], dim=-1)
+        soft, prob, cidx, ctype = b200_C.render.mesh.dibr_soft_mask_forward_cuda(
+            fvi_m, bb, face_idx, sigmainv, knum, multiplier)
+        assert torch.allclose(soft.cpu(), torch.from_numpy(g[key + "soft_mask"]), atol=1e-5, rtol=1e-5)
+        assert torch.equal(cidx.cpu(), torch.from_numpy(g[key + "close_face_idx"][..., :knum].astype(np.int64)))
+        assert torch.allclose(prob.cpu(), torch.from_numpy(g[key + "close_face_prob"][..., :knum]),
+                              atol=1e-5, rtol=1e-5)
+        if not flip:
+            mism = ctype.cpu() != torch.from_numpy(g[key + "close_face_dist_type"][..., :knum])
+            assert mism.sum() / mism.numel() <= 0.01
+    t_fvi = fvi.detach().clone().requires_grad_(True)
+    soft2 = dibr_soft_mask(t_fvi, face_idx, sigmainv, boxlen, knum, 1000)
+    _mask_iou(soft2, face_idx).backward()
+    ref = g[key + "grad_fvi"]
+    if flip:
+        ref = ref[:, :, ::-1]
+    assert torch.allclose(t_fvi.grad.cpu(), torch.from_numpy(np.ascontiguousarray(ref)), rtol=1e-1, atol=1e-1)
+    assert rel_err(N(t_fvi.grad), ref) <= 2e-3
+
+
+def test_operator_level_vs_oracle():
+    """The four `_C` operators with the reference's packed arguments (rasterization.py:308-339)."""
+    fvz, fvi, fnz = synthetic.icosphere_views(3, 3, seed=31)
+    B, F = fvz.shape[:2]
+    D = 4
+    ff = synthetic.random_features(B, F, D, seed=3)
+    H, W = 50, 66
+    valid = fnz >= 0
+    valid[1] = False                      # a mesh with no valid face at all
+    b_idx, f_idx = np.nonzero(valid)
+    first = np.zeros(B + 1, np.int64)
+    np.cumsum(valid.sum(1), out=first[1:])
+    xy = np.ascontiguousarray(fvi[b_idx, f_idx] * np.float32(1000))
+    z = np.ascontiguousarray(fvz[b_idx, f_idx])
+    feat = np.ascontiguousarray(ff[b_idx, f_idx])
+    bbox = np.ascontiguousarray(np.concatenate([xy.min(1), xy.max(1)], 1))
+    out, sel, w = b200_C.render.mesh.packed_rasterize_forward_cuda(
+        H, W, T(z), T(xy), T(bbox), T(feat), T(first), 1000, 1e-8)
+    o_out, o_sel, o_w = oracle.packed_rasterize_forward(H, W, z, xy, bbox, feat, first, 1000, 1e-8)
+    assert np.array_equal(N(sel), o_sel)
+    assert (o_sel[1] == -1).all() and (o_sel[0] >= 0).any()
+    assert np.array_equal(N(w).view(np.uint32), o_w.view(np.uint32))
+    np.testing.assert_allclose(N(out), o_out, rtol=0, atol=1e-6)
+    # backward operator (original ids, unscaled coordinates)
+    _, face_idx, wts = oracle.rasterize(H, W, fvz, fvi, ff, valid, return_weights=True)
+    rng = np.random.default_rng(5)
+    g = rng.uniform(size=(B, H, W, D)).astype(np.float32)
+    gxy, gff = b200_C.render.mesh.rasterize_backward_cuda(
+        T(g), T(np.zeros_like(g)), T(face_idx), T(wts), T(fvi), T(ff), 1e-8)
+    o_gxy, o_gff = oracle.rasterize_backward(g, face_idx, wts, fvi, ff)
+    assert rel_err(N(gxy), o_gxy) <= GRAD_REL and rel_err(N(gff), o_gff) <= GRAD_REL
+
+
+@pytest.mark.parametrize("D", [1, 2, 5, 9])
+def test_feature_dims(D):
+    fvz, fvi, fnz = synthetic.icosphere_views(1, 2, seed=8)
+    B, F = fvz.shape[:2]
+    ff = synthetic.random_features(B, F, D, seed=2)
+    H, W = 48, 48
+    rng = np.random.default_rng(1)
+    g = rng.uniform(size=(B, H, W, D)).astype(np.float32)
+    t_fvi, t_ff = T(fvi, True), T(ff, True)
+    feat, idx = rasterize(H, W, T(fvz), t_fvi, t_ff)
+    feat.backward(T(g))
+    o_feat, o_idx, o_w = oracle.rasterize(H, W, fvz, fvi, ff, None, return_weights=True)
+    assert np.array_equal(N(idx), o_idx)
+    np.testing.assert_allclose(N(feat), o_feat, rtol=0, atol=1e-6)
+    o_gxy, o_gff = oracle.rasterize_backward(g, o_idx, o_w, fvi, ff)
+    assert rel_err(N(t_fvi.grad), o_gxy) <= GRAD_REL and rel_err(N(t_ff.grad), o_gff) <= GRAD_REL
+
+
+def test_edge_cases():
+    """Ragged / degenerate inputs: exact ties, zero-area faces, faces off screen, all faces
+    culled, tiny and non-multiple-of-16 images, knum = 1."""
+    fvz, fvi, fnz = synthetic.triangle_soup(1, 40, seed=9, coverage=6.0)
+    fvi = np.concatenate([fvi, fvi[:, :10], fvi[:, :5] * 0 + 0.3, fvi[:, :5] + 5.0], 1)
+    fvz = np.concatenate([fvz, fvz[:, :10], fvz[:, :5], fvz[:, :5]], 1)
+    fnz = np.ones(fvz.shape[:2], np.float32)
+    B, F = fvz.shape[:2]
+    ff = synthetic.random_features(B, F, 2, seed=1)
+    for H, W in ((33, 29), (16, 16), (1, 1), (5, 70), (17, 15)):
+        for knum in (1, 30):
+            feat, soft, idx = dibr_rasterization(H, W, T(fvz), T(fvi), T(ff), T(fnz), knum=knum)
+            o_feat, o_soft, o_idx = oracle.dibr_rasterization(H, W, fvz, fvi, ff, fnz, knum=knum)
+            assert np.array_equal(N(idx), o_idx), (H, W)
+            np.testing.assert_allclose(N(feat), o_feat, rtol=0, atol=1e-6)
+            np.testing.assert_allclose(N(soft), o_soft, rtol=0, atol=1e-6)
+    # every face back-facing: nothing rasterized, soft mask still sees all faces (dibr.py:200-208)
+    feat, soft, idx = dibr_rasterization(40, 40, T(fvz), T(fvi), T(ff), T(-fnz))
+    o_feat, o_soft, o_idx = oracle.dibr_rasterization(40, 40, fvz, fvi, ff, -fnz)
+    assert (N(idx) == -1).all() and np.array_equal(N(idx), o_idx)
+    np.testing.assert_allclose(N(soft), o_soft, rtol=0, atol=1e-6)
+    assert (o_soft > 0).any()
+
+
+def test_soft_mask_dense_overflow_path():
+    """> 1024 enlarged faces over one tile: exercises the windowed first-K walk."""
+    rng = np.random.default_rng(4)
+    F = 3000
+    c = rng.uniform(-0.05, 0.05, size=(1, F, 1, 2))
+    fvi = (c + rng.normal(scale=0.004, size=(1, F, 3, 2))).astype(np.float32)
+    fvz = rng.uniform(-3, -1, size=(1, F, 3)).astype(np.float32)
+    fnz = np.ones((1, F), np.float32)
+    ff = synthetic.random_features(1, F, 1, seed=0)
+    H = W = 64
+    for knum in (30, 2000):
+        t_fvi = T(fvi, True)
+        feat, soft, idx = dibr_rasterization(H, W, T(fvz), t_fvi, T(ff), T(fnz), boxlen=0.1, knum=knum)
+        o_feat, o_soft, o_idx, o_w = oracle.dibr_rasterization(H, W, fvz, fvi, ff, fnz, boxlen=0.1,
+                                                              knum=knum, return_weights=True)
+        assert np.array_equal(N(idx), o_idx)
+        np.testing.assert_allclose(N(soft), o_soft, rtol=0, atol=1e-5)
+        g_soft = rng.uniform(size=(1, H, W)).astype(np.float32)
+        soft.backward(T(g_soft))
+        o_g = oracle.dibr_soft_mask_backward(g_soft, fvi, o_idx, 7000, 0.1, knum, 1000.)
+        assert rel_err(N(t_fvi.grad), o_g) <= 2e-5
+
+
+def test_errors_like_reference():
+    fvz, fvi, fnz = synthetic.icosphere_views(1, 1, seed=1)
+    ff = synthetic.random_features(1, fvz.shape[1], 2)
+    with pytest.raises(ValueError):
+        rasterize(8, 8, T(fvz), T(fvi), T(ff), backend="nvdiffrast")
+    with pytest.raises(ValueError):
+        dibr_rasterization(8, 8, T(fvz), T(fvi), T(ff), T(fnz), rast_backend="nvdiffrast_fwd")
+    with pytest.raises(RuntimeError):   # CPU tensors: no CPU path (rasterization.cpp:95-102)
+        rasterize(8, 8, torch.from_numpy(fvz), torch.from_numpy(fvi), torch.from_numpy(ff))
+    with pytest.raises(RuntimeError):   # double not implemented
+        rasterize(8, 8, T(fvz).double(), T(fvi).double(), T(ff).double())
+    with pytest.raises(RuntimeError):   # non-contiguous operator argument (checkAllContiguous)
+        b200_C.render.mesh.rasterize_backward_cuda(
+            torch.zeros(1, 8, 8, 2, device=DEV).transpose(1, 2), torch.zeros(1, 8, 8, 2, device=DEV),
+            torch.zeros(1, 8, 8, dtype=torch.long, device=DEV), torch.zeros(1, 8, 8, 3, device=DEV),
+            T(fvi), T(ff), 1e-8)
+
+
+def test_full_size_properties():
+    """BASELINE configs[3] per-GPU shape cut to 4 views (1024^2, 20480 faces): properties that
+    need no oracle — determinism of the forward, composition equality, background consistency,
+    interpolation of constant features, translation of the image by whole tiles."""
+    fvz, fvi, fnz = synthetic.icosphere_views(4, 5, seed=77)
+    B, F = fvz.shape[:2]
+    H = W = 1024
+    ones = np.ones((B, F, 3, 1), np.float32)
+    uv = synthetic.random_features(B, F, 2, seed=3)
+    args = (T(fvz), T(fvi), [T(uv), T(ones)], T(fnz))
+    (uv1, m1), s1, i1 = dibr_rasterization(H, W, *args)
+    (uv2, m2), s2, i2 = dibr_rasterization(H, W, *args)
+    assert torch.equal(i1, i2) and torch.equal(uv1, uv2) and torch.equal(s1, s2)
+    cov = i1 >= 0
+    assert 0.2 < cov.float().mean().item() < 0.8
+    # constant feature interpolates to w0+w1+w2 = 1 (within rounding) on covered, 0 elsewhere
+    assert torch.all((m1[..., 0] - 1).abs()[cov] < 1e-5) and torch.all(m1[..., 0][~cov] == 0)
+    assert torch.all(s1[cov] == 1) and torch.all((s1 >= 0) & (s1 <= 1))
+    # only front-facing faces are drawn
+    fn = T(fnz)
+    assert torch.all(torch.gather(fn, 1, i1.clamp(min=0).reshape(B, -1)).reshape(B, H, W)[cov] >= 0)
+    # the soft mask decays away from the silhouette: pixels farther than boxlen from any face are 0
+    (b_uv, b_m), b_idx = rasterize(H, W, args[0], args[1], args[2], fn >= 0)
+    assert torch.equal(b_idx, i1) and torch.equal(b_uv, uv1)
+    # one view against the CPU oracle on a 128x1024 strip would take minutes; instead compare a
+    # 1-view 256x256 render of the same mesh (same faces, different sampling) exactly
+    f2, s2b, i2b = dibr_rasterization(256, 256, args[0][:1], args[1][:1], T(uv[:1]), args[3][:1])
+    o_f, o_s, o_i = oracle.dibr_rasterization(256, 256, fvz[:1], fvi[:1], uv[:1], fnz[:1])
+    assert np.array_equal(N(i2b), o_i)
+    np.testing.assert_allclose(N(s2b), o_s, rtol=0, atol=1e-5)
+    np.testing.assert_allclose(N(f2), o_f, rtol=0, atol=1e-5)
