@@ -47,6 +47,16 @@ int dibr_b200_version(void);
  * in all views together on a height x width image. */
 size_t dibr_b200_workspace_bytes(int batch, int64_t total_faces, int height, int width);
 
+/* Minimum scratch + a soft-mask hit cache for `cache_tiles` 16x16 screen tiles
+ * (3072*knum + 16 bytes each).  Any workspace larger than the minimum is used by
+ * dibr_b200_forward (mode & SOFT_MASK) to record, per tile that has any, the
+ * (pixel, face, probability, distance type) hits — what the reference stores as
+ * 13*knum bytes for EVERY pixel (dibr.py:49-54) — so that dibr_b200_backward with
+ * bins_valid = 1 streams over them instead of recomputing the neighbour walk.
+ * Tiles that do not fit are recomputed in backward; results are identical. */
+size_t dibr_b200_workspace_bytes_cached(int batch, int64_t total_faces, int height, int width,
+                                        int knum, int64_t cache_tiles);
+
 /*
  * Fused forward on the public-API tensors.
  * Replaces: kaolin/render/mesh/rasterization.py:273-352 (RasterizeCuda.forward:

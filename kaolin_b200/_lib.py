@@ -33,6 +33,7 @@ _sz = ctypes.c_size_t
 SIGNATURES = {
     "dibr_b200_version": (_i, []),
     "dibr_b200_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
+    "dibr_b200_workspace_bytes_cached": (_sz, [_i, _i64, _i, _i, _i, _i64]),
     "dibr_b200_forward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _f, _f, _i,
                                _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dibr_b200_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -54,9 +54,17 @@ struct Scene {
   int L;
   int ntx[kMaxLevels], nty[kMaxLevels], bin_base[kMaxLevels];
   int NB;                 // bins per view (all levels)
-  int* cnt;               // [2][B][NB]
+  int* cnt;               // [2][B][NB] (+ pool_ctr right behind it: one memset clears both)
   int* off;               // [2][B][NB]
   int4* entries;          // [2][4*NF]  {face, x_lo|x_hi<<16, y_lo|y_hi<<16, 0}
+  // soft-mask hit cache: what the reference keeps as 13*knum bytes for EVERY pixel
+  // (close_face_{prob,idx,dist_type}) is kept only for tiles that have hits
+  int pool_tiles;         // capacity in tiles (0 = disabled)
+  int pool_K;             // knum the blocks are sized for (block = 3 * 256*K words)
+  int* pool_ctr;          // [1] blocks handed out
+  int4* pool_hdr;         // [pool_tiles] {b, tx, ty, hits}
+  uint32_t* pool_data;    // [pool_tiles][3][256*K]: face | prob bits | lx|ly<<4|(dist_type)<<8
+  uint8_t* tile_mode;     // [B*nty*ntx] 0: no soft work, 1: hits cached, 2: recompute in backward
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -256,12 +264,7 @@ struct TileCtx {
 
 __device__ __forceinline__ TileCtx make_tile_ctx(const Scene& s) {
   TileCtx c;
-  const int tiles = s.ntx[0] * s.nty[0];
-  const int t = blockIdx.x;
-  c.b = t / tiles;
-  const int r = t - c.b * tiles;
-  c.ty = r / s.ntx[0];
-  c.tx = r - c.ty * s.ntx[0];
+  c.tx = blockIdx.x; c.ty = blockIdx.y; c.b = blockIdx.z;   // grid = (tiles_x, tiles_y, views)
   c.tile_x0 = c.tx * kTile;
   c.tile_y0 = c.ty * kTile;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -280,13 +283,14 @@ __device__ __forceinline__ TileCtx make_tile_ctx(const Scene& s) {
 
 // bins above tile (tx,ty) in bin set `set`
 struct BinRef { const int4* ptr; int n; };
-__device__ __forceinline__ BinRef tile_bin(const Scene& s, const TileCtx& c, int set, int l) {
+__device__ __forceinline__ BinRef tile_bin(const Scene& s, int b, int tx, int ty, int64_t fbase,
+                                           int set, int l) {
   const int sh = 2 * l;
-  const int bin = s.bin_base[l] + (c.ty >> sh) * s.ntx[l] + (c.tx >> sh);
-  const size_t ci = ((size_t)set * s.B + c.b) * s.NB + bin;
+  const int bin = s.bin_base[l] + (ty >> sh) * s.ntx[l] + (tx >> sh);
+  const size_t ci = ((size_t)set * s.B + b) * s.NB + bin;
   BinRef r;
   r.n = s.cnt[ci];
-  r.ptr = s.entries + (size_t)set * 4 * s.NF + 4 * c.fbase + s.off[ci];
+  r.ptr = s.entries + (size_t)set * 4 * s.NF + 4 * fbase + s.off[ci];
   return r;
 }
 
@@ -302,9 +306,25 @@ struct TileSmem {
   unsigned long long sorted[kSoftCap];
   float acc[kChunk][6];                  // soft-mask backward per-candidate sums
   unsigned long long bar[2];
+  BinRef bin[2][kMaxLevels];             // the tile's bins (set, level): filled once by warp 0
   int ncand;
   int nsoft;
+  int nent;                              // hits appended to the cache block
+  int pool_slot;                         // cache block of this tile (-1: none)
 };
+
+// Lanes 0..L-1 / 8..8+L-1 of warp 0 look up the tight / large bins of the tile.
+__device__ __forceinline__ void load_bin_table(const Scene& s, const TileCtx& c, TileSmem& sm) {
+  const int tid = threadIdx.x;
+  if (tid < 16) {
+    const int set = tid >> 3, l = tid & 7;
+    if (l < kMaxLevels) {
+      BinRef r; r.ptr = nullptr; r.n = 0;
+      if (l < s.L) r = tile_bin(s, c.b, c.tx, c.ty, c.fbase, set, l);
+      sm.bin[set][l] = r;
+    }
+  }
+}
 
 // ---------------------------------------------------------------------------
 // Rasterization of one tile: walks the "tight" bins of every level.
@@ -315,40 +335,36 @@ __device__ __forceinline__ void raster_tile(const Scene& s, const TileCtx& c, co
   const int tid = threadIdx.x, lane = tid & 31;
   o.z = -INFINITY; o.f = -1; o.w0 = o.w1 = o.w2 = 0.f;
 
-  BinRef bins[kMaxLevels];
-  int nchunks = 0;
+  // The (<= 6) tight bins above the tile form one virtual list, streamed in
+  // rounds of kChunk entries: one mbarrier per round, one bulk copy per level piece.
+  int nl[kMaxLevels];
+  int total = 0;
 #pragma unroll
-  for (int l = 0; l < kMaxLevels; ++l) {
-    if (l < s.L) { bins[l] = tile_bin(s, c, 0, l); nchunks += (bins[l].n + kChunk - 1) / kChunk; }
-    else { bins[l].ptr = nullptr; bins[l].n = 0; }
-  }
-  if (nchunks == 0) return;  // uniform for the CTA
+  for (int l = 0; l < kMaxLevels; ++l) { nl[l] = sm.bin[0][l].n; total += nl[l]; }
+  if (total == 0) return;  // uniform for the CTA
+  const int nrounds = (total + kChunk - 1) / kChunk;
 
-  auto chunk_src = [&](int k, const int4*& src, int& cnt) {
+  auto issue = [&](int k) {  // thread 0 only
+    const int lo = k * kChunk, hi = min(total, lo + kChunk);
+    unsigned long long* bar = &sm.bar[k & 1];
+    mbar_expect_tx(bar, (uint32_t)(hi - lo) * 16u);
+    int start = 0;
 #pragma unroll
     for (int l = 0; l < kMaxLevels; ++l) {
-      const int nc = (bins[l].n + kChunk - 1) / kChunk;
-      if (k < nc) { src = bins[l].ptr + (size_t)k * kChunk; cnt = min(kChunk, bins[l].n - k * kChunk); return; }
-      k -= nc;
+      const int a = max(lo, start), b = min(hi, start + nl[l]);
+      if (b > a) tma_load_1d(&sm.stage[k & 1][a - lo], sm.bin[0][l].ptr + (a - start), (uint32_t)(b - a) * 16u, bar);
+      start += nl[l];
     }
-    src = nullptr; cnt = 0;
-  };
-  auto issue = [&](int k) {  // thread 0 only
-    const int4* src; int cnt;
-    chunk_src(k, src, cnt);
-    mbar_expect_tx(&sm.bar[k & 1], (uint32_t)cnt * 16u);
-    tma_load_1d(sm.stage[k & 1], src, (uint32_t)cnt * 16u, &sm.bar[k & 1]);
   };
 
   if (tid == 0) issue(0);
-  for (int k = 0; k < nchunks; ++k) {
+  for (int k = 0; k < nrounds; ++k) {
     if (tid == 0) {
       sm.ncand = 0;
-      if (k + 1 < nchunks) issue(k + 1);  // buffer (k+1)&1 was released by the sync ending iteration k-1
+      if (k + 1 < nrounds) issue(k + 1);  // buffer (k+1)&1 was released by the sync ending round k-1
     }
     __syncthreads();
-    const int4* src; int cnt;
-    chunk_src(k, src, cnt);
+    const int cnt = min(kChunk, total - k * kChunk);
     mbar_wait(&sm.bar[k & 1], (uint32_t)((k >> 1) & 1));
 
     // cull against the tile, gather the face, stage the record
@@ -384,7 +400,7 @@ __device__ __forceinline__ void raster_tile(const Scene& s, const TileCtx& c, co
       // reference: strict '>' in ascending face order == (z, lowest index) maximum
       if (!(zv <= o.z) || (zv == o.z && f < o.f)) { o.z = zv; o.f = f; o.w0 = w0; o.w1 = w1; o.w2 = w2; }
     }
-    __syncthreads();
+    if (k + 1 < nrounds) __syncthreads();
   }
 }
 
@@ -398,7 +414,7 @@ __device__ __forceinline__ int soft_collect(const Scene& s, const TileCtx& c, Ti
   if (tid == 0) sm.nsoft = 0;
   __syncthreads();
   for (int l = 0; l < s.L; ++l) {
-    const BinRef bin = tile_bin(s, c, 1, l);
+    const BinRef bin = sm.bin[1][l];
     for (int base = 0; base < bin.n; base += kThreads) {
       const int i = base + tid;
       uint32_t m = 0; int f = 0;
@@ -427,19 +443,32 @@ struct SoftFwdOut {
   float* prob; int64_t* idx; uint8_t* type;  // K-lists (nullable)
 };
 
+__device__ __forceinline__ size_t tile_linear(const Scene& s, const TileCtx& c) {
+  return ((size_t)c.b * s.nty[0] + c.ty) * s.ntx[0] + c.tx;
+}
+
+// CACHE (forward only): every hit (pixel, face, prob, dist_type) is appended to the
+// tile's block of the hit cache so that the backward pass is a dense stream over
+// hits instead of a second walk (the reference stores 13*knum bytes per pixel).
 template <bool BWD, bool KLISTS>
 __device__ __forceinline__ void soft_tile(const Scene& s, const TileCtx& c, TileSmem& sm, bool active,
-                                          float sigmainv, int K, float& allprob, int& kid,
+                                          float sigmainv, int K, bool cache, float& allprob, int& kid,
                                           const SoftFwdOut& kl, float dLdp, float soft_saved,
                                           float* grad_xy) {
   const int tid = threadIdx.x, lane = tid & 31;
   allprob = 1.0f;
   kid = 0;
-  if (!__syncthreads_or(active)) return;
+  if (!__syncthreads_or(active)) {
+    if (!BWD && cache && tid == 0) s.tile_mode[tile_linear(s, c)] = 0;
+    return;
+  }
   if (BWD) {
     for (int i = tid; i < kChunk * 6; i += kThreads) (&sm.acc[0][0])[i] = 0.f;
   }
   const int maxf = s.first ? (int)(__ldg(s.first + c.b + 1) - c.fbase) : s.F;
+  const size_t E = (size_t)256 * s.pool_K;
+  uint32_t* blk = nullptr;
+  bool first_window = true;
   int lo = -1;
   while (true) {
     int hi = 0x7fffffff;
@@ -453,6 +482,21 @@ __device__ __forceinline__ void soft_tile(const Scene& s, const TileCtx& c, Tile
       }
       hi = L;
       n = soft_collect<false>(s, c, sm, lo, hi);
+    }
+    if (!BWD && cache && first_window) {
+      first_window = false;
+      if (tid == 0) {
+        int slot = -1;
+        if (n > 0) {
+          slot = atomicAdd(s.pool_ctr, 1);
+          if (slot >= s.pool_tiles) slot = -1;
+        }
+        sm.pool_slot = slot;
+        sm.nent = 0;
+        s.tile_mode[tile_linear(s, c)] = n == 0 ? 0 : (slot >= 0 ? 1 : 2);
+      }
+      __syncthreads();
+      if (sm.pool_slot >= 0) blk = s.pool_data + (size_t)sm.pool_slot * 3 * E;
     }
     // rank sort by face index (keys are unique: a face lives in one level, a tile reads one bin per level)
     for (int j = tid; j < n; j += kThreads) {
@@ -479,13 +523,14 @@ __device__ __forceinline__ void soft_tile(const Scene& s, const TileCtx& c, Tile
       for (int j = 0; j < cn; ++j) {
         const bool hit = active && kid < K && ((sm.cmask[j] & c.sel) == c.sel);
         float g[6];
+        float prob = 0.f;
+        int edgeid = 0;
         if (hit) {
           const float4 q0 = sm.cxy0[j];
           const float2 q1 = sm.cxy1[j];
           const float v[6] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y};
-          int edgeid;
           const float d2 = soft_min_dist(c.x0, c.y0, v, s.multiplier, edgeid);
-          const float prob = soft_prob(d2, sigmainv, s.multiplier);
+          prob = soft_prob(d2, sigmainv, s.multiplier);
           if (!BWD) {
             allprob = soft_accumulate(allprob, prob);
             if (KLISTS) {
@@ -496,6 +541,20 @@ __device__ __forceinline__ void soft_tile(const Scene& s, const TileCtx& c, Tile
             soft_backward_terms(c.x0, c.y0, v, edgeid, prob, soft_saved, dLdp, sigmainv, s.multiplier, g);
           }
           ++kid;
+        }
+        if (!BWD && blk != nullptr) {
+          const unsigned vote = __ballot_sync(kFull, hit);
+          if (vote) {
+            int wb = 0;
+            if (lane == 0) wb = atomicAdd(&sm.nent, __popc(vote));
+            wb = __shfl_sync(kFull, wb, 0);
+            if (hit) {
+              const size_t e = (size_t)wb + __popc(vote & ((1u << lane) - 1u));
+              blk[e] = (uint32_t)sm.cface[j];
+              blk[E + e] = __float_as_uint(prob);
+              blk[2 * E + e] = (uint32_t)c.lx | ((uint32_t)c.ly << 4) | ((uint32_t)(edgeid + 1) << 8);
+            }
+          }
         }
         if (BWD) {
           if (__any_sync(kFull, hit)) {
@@ -525,6 +584,8 @@ __device__ __forceinline__ void soft_tile(const Scene& s, const TileCtx& c, Tile
     if (hi == 0x7fffffff || all_done) break;
     lo = hi;
   }
+  if (!BWD && blk != nullptr && tid == 0)
+    s.pool_hdr[sm.pool_slot] = make_int4(c.b, c.tx, c.ty, sm.nent);
 }
 
 // ---------------------------------------------------------------------------
@@ -535,6 +596,7 @@ struct FwdArgs {
   int D;
   const float* feat;        // (NF,3,D)
   float sigmainv; int K;
+  int cache;                // fill the soft-mask hit cache
   float* out_feat; int64_t* idx; float* out_w; float* out_soft;  // idx: output if RASTER else input
   SoftFwdOut kl;
 };
@@ -544,11 +606,10 @@ __global__ void __launch_bounds__(kThreads) dibr_tile_fwd_kernel(const __grid_co
   __shared__ __align__(128) TileSmem sm;
   const Scene& s = a.s;
   const int tid = threadIdx.x;
-  if (RASTER) {
-    if (tid == 0) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_fence_init(); }
-    __syncthreads();
-  }
   const TileCtx c = make_tile_ctx(s);
+  if (RASTER && tid == 32) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_fence_init(); }
+  load_bin_table(s, c, sm);
+  __syncthreads();
   int best_f;
   if (RASTER) {
     RasterOut o;
@@ -573,7 +634,8 @@ __global__ void __launch_bounds__(kThreads) dibr_tile_fwd_kernel(const __grid_co
   if (SOFT) {
     const bool active = c.in_img && best_f < 0;
     float allprob; int kid;
-    soft_tile<false, KLISTS>(s, c, sm, active, a.sigmainv, a.K, allprob, kid, a.kl, 0.f, 0.f, nullptr);
+    soft_tile<false, KLISTS>(s, c, sm, active, a.sigmainv, a.K, !KLISTS && a.cache != 0, allprob, kid,
+                             a.kl, 0.f, 0.f, nullptr);
     if (c.in_img) {
       a.out_soft[c.pix] = active ? soft_finish(allprob) : 1.0f;
       if (KLISTS) {  // padding the reference gets from at::zeros / at::full(-1)
@@ -587,10 +649,12 @@ __global__ void __launch_bounds__(kThreads) dibr_tile_fwd_kernel(const __grid_co
 }
 
 // ---------------------------------------------------------------------------
-// Soft-mask backward (recompute) tile kernel.
+// Soft-mask backward.  (1) dense kernel over the hit cache; (2) the recompute tile
+// kernel for tiles the cache could not hold (tile_mode == 2) or when no cache exists.
 struct SoftBwdArgs {
   Scene s;
   float sigmainv; int K;
+  int only_mode2;            // 1: skip tiles whose hits are cached (or that have none)
   const float* grad_soft; const float* soft; const int64_t* idx;
   float* grad_xy;
 };
@@ -599,6 +663,9 @@ __global__ void __launch_bounds__(kThreads) dibr_tile_soft_bwd_kernel(const __gr
   __shared__ __align__(128) TileSmem sm;
   const Scene& s = a.s;
   const TileCtx c = make_tile_ctx(s);
+  if (a.only_mode2 && s.tile_mode[tile_linear(s, c)] != 2) return;
+  load_bin_table(s, c, sm);
+  __syncthreads();
   bool active = false;
   float dLdp = 0.f, soft_saved = 0.f;
   if (c.in_img && a.idx[c.pix] < 0) {
@@ -608,7 +675,50 @@ __global__ void __launch_bounds__(kThreads) dibr_tile_soft_bwd_kernel(const __gr
   }
   float allprob; int kid;
   SoftFwdOut none = {nullptr, nullptr, nullptr};
-  soft_tile<true, false>(s, c, sm, active, a.sigmainv, a.K, allprob, kid, none, dLdp, soft_saved, a.grad_xy);
+  soft_tile<true, false>(s, c, sm, active, a.sigmainv, a.K, false, allprob, kid, none, dLdp, soft_saved,
+                         a.grad_xy);
+}
+
+template <int N>
+__device__ __forceinline__ void reduce_peers(unsigned peers, float (&v)[N]);
+
+__global__ void __launch_bounds__(kThreads) soft_bwd_dense_kernel(const __grid_constant__ SoftBwdArgs a) {
+  const Scene& s = a.s;
+  const int used = min(*s.pool_ctr, s.pool_tiles);
+  if ((int)blockIdx.x >= used) return;
+  const int4 h = s.pool_hdr[blockIdx.x];  // b, tx, ty, hits
+  const size_t E = (size_t)256 * s.pool_K;
+  const uint32_t* blk = s.pool_data + (size_t)blockIdx.x * 3 * E;
+  const int64_t fbase = view_fbase(s, h.x);
+  const int tid = threadIdx.x, lane = tid & 31;
+  for (int base = 0; base < h.w; base += kThreads) {
+    const int t = base + tid;
+    const bool valid = t < h.w;
+    int face = -1 - lane;
+    float g[6];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) g[q] = 0.f;
+    if (valid) {
+      face = (int)blk[t];
+      const float prob = __uint_as_float(blk[E + t]);
+      const uint32_t meta = blk[2 * E + t];
+      const int px = h.y * kTile + (int)(meta & 15u), py = h.z * kTile + (int)((meta >> 4) & 15u);
+      const int64_t pix = ((int64_t)h.x * s.H + py) * s.W + px;
+      float v[6];
+      load_xy(s, fbase + face, v);
+      soft_backward_terms(pix_x(s.grid, px), pix_y(s.grid, py), v, (int)(meta >> 8) - 1, prob,
+                          __ldg(a.soft + pix), __ldg(a.grad_soft + pix), a.sigmainv, s.multiplier, g);
+    }
+    // hits were appended candidate by candidate: neighbouring lanes mostly share the face
+    const unsigned peers = __match_any_sync(kFull, face);
+    reduce_peers<6>(peers, g);
+    if (valid && (peers & ((1u << lane) - 1u)) == 0) {
+      float2* gx = reinterpret_cast<float2*>(a.grad_xy + (fbase + face) * 6);
+      if (g[0] != 0.f || g[1] != 0.f) atomicAdd(gx, make_float2(g[0], g[1]));
+      if (g[2] != 0.f || g[3] != 0.f) atomicAdd(gx + 1, make_float2(g[2], g[3]));
+      if (g[4] != 0.f || g[5] != 0.f) atomicAdd(gx + 2, make_float2(g[4], g[5]));
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -644,11 +754,7 @@ struct RasterBwdArgs {
 
 template <int DT>  // DT > 0: feature dim known at compile time; 0: runtime loop
 __global__ void __launch_bounds__(kThreads) raster_bwd_kernel(const __grid_constant__ RasterBwdArgs a) {
-  const int tiles = a.ntx * a.nty;
-  const int t = blockIdx.x;
-  const int b = t / tiles;
-  const int r = t - b * tiles;
-  const int ty = r / a.ntx, tx = r - ty * a.ntx;
+  const int tx = blockIdx.x, ty = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int px = tx * kTile + (((warp & 1) << 3) | (lane & 7));
   const int py = ty * kTile + (((warp >> 1) << 2) | (lane >> 3));
@@ -662,18 +768,15 @@ __global__ void __launch_bounds__(kThreads) raster_bwd_kernel(const __grid_const
   const int64_t face = (int64_t)b * a.F + (cov ? f : 0);
 
   float w0 = 0.f, w1 = 0.f, w2 = 0.f;
-  float dw1[6], dw2[6], k3 = 1.f;
-#pragma unroll
-  for (int i = 0; i < 6; ++i) { dw1[i] = 0.f; dw2[i] = 0.f; }
+  RasterBwdGeom G;
   if (cov) {
     const float* wp = a.w + pix * 3;
     w0 = wp[0]; w1 = wp[1]; w2 = wp[2];
     const float2* pp = reinterpret_cast<const float2*>(a.xy + face * 6);
     const float2 pa = __ldg(pp), pb = __ldg(pp + 1), pc = __ldg(pp + 2);
     const float p[6] = {pa.x, pa.y, pb.x, pb.y, pc.x, pc.y};
-    raster_backward_geom(p, w0, w1, w2, a.eps, dw1, dw2, k3);
+    raster_backward_geom(p, w0, w1, w2, a.eps, G);
   }
-  const float inv_k3sq = 1.f / (k3 * k3);
   // lanes without a face get unique negative keys so they never merge
   const unsigned peers = __match_any_sync(kFull, cov ? (int)f : -1 - lane);
   const bool leader = (peers & ((1u << lane) - 1u)) == 0;
@@ -682,18 +785,20 @@ __global__ void __launch_bounds__(kThreads) raster_bwd_kernel(const __grid_const
 
   if (DT > 0) {
     float v[6 + 3 * (DT > 0 ? DT : 1)];
-    float S1 = 0.f, S2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 6; ++j) v[j] = 0.f;
 #pragma unroll
     for (int d = 0; d < DT; ++d) {
-      float g = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-      if (cov) { g = gp[d]; c0 = __ldg(cf + d); c1 = __ldg(cf + DT + d); c2 = __ldg(cf + 2 * DT + d); }
-      const float dl = g * inv_k3sq;
-      S1 += dl * (c1 - c0);
-      S2 += dl * (c2 - c0);
+      float g = 0.f;
+      if (cov) {
+        g = gp[d];
+        float t6[6];
+        raster_backward_feature(G, g, __ldg(cf + d), __ldg(cf + DT + d), __ldg(cf + 2 * DT + d), t6);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) v[j] += t6[j];
+      }
       v[6 + d] = g * w0; v[6 + DT + d] = g * w1; v[6 + 2 * DT + d] = g * w2;
     }
-#pragma unroll
-    for (int j = 0; j < 6; ++j) v[j] = S1 * dw1[j] + S2 * dw2[j];
     reduce_peers<6 + 3 * (DT > 0 ? DT : 1)>(peers, v);
     if (leader && cov) {
       float2* gx = reinterpret_cast<float2*>(a.grad_xy + face * 6);
@@ -705,13 +810,18 @@ __global__ void __launch_bounds__(kThreads) raster_bwd_kernel(const __grid_const
       for (int j = 0; j < 3 * DT; ++j) atomicAdd(gf + j, v[6 + j]);
     }
   } else {
-    float S1 = 0.f, S2 = 0.f;
+    float vx[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) vx[j] = 0.f;
     for (int d = 0; d < D; ++d) {
-      float g = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-      if (cov) { g = gp[d]; c0 = __ldg(cf + d); c1 = __ldg(cf + D + d); c2 = __ldg(cf + 2 * D + d); }
-      const float dl = g * inv_k3sq;
-      S1 += dl * (c1 - c0);
-      S2 += dl * (c2 - c0);
+      float g = 0.f;
+      if (cov) {
+        g = gp[d];
+        float t6[6];
+        raster_backward_feature(G, g, __ldg(cf + d), __ldg(cf + D + d), __ldg(cf + 2 * D + d), t6);
+#pragma unroll
+        for (int j = 0; j < 6; ++j) vx[j] += t6[j];
+      }
       float v[3] = {g * w0, g * w1, g * w2};
       reduce_peers<3>(peers, v);
       if (leader && cov) {
@@ -719,15 +829,12 @@ __global__ void __launch_bounds__(kThreads) raster_bwd_kernel(const __grid_const
         atomicAdd(gf + d, v[0]); atomicAdd(gf + D + d, v[1]); atomicAdd(gf + 2 * D + d, v[2]);
       }
     }
-    float v[6];
-#pragma unroll
-    for (int j = 0; j < 6; ++j) v[j] = S1 * dw1[j] + S2 * dw2[j];
-    reduce_peers<6>(peers, v);
+    reduce_peers<6>(peers, vx);
     if (leader && cov) {
       float2* gx = reinterpret_cast<float2*>(a.grad_xy + face * 6);
-      atomicAdd(gx, make_float2(v[0], v[1]));
-      atomicAdd(gx + 1, make_float2(v[2], v[3]));
-      atomicAdd(gx + 2, make_float2(v[4], v[5]));
+      atomicAdd(gx, make_float2(vx[0], vx[1]));
+      atomicAdd(gx + 1, make_float2(vx[2], vx[3]));
+      atomicAdd(gx + 2, make_float2(vx[4], vx[5]));
     }
   }
 }
@@ -770,8 +877,6 @@ __global__ void __launch_bounds__(256) soft_bwd_lists_kernel(const __grid_consta
 
 // ---------------------------------------------------------------------------
 // Host side.
-struct Workspace { int* cnt; int* off; int4* entries; };
-
 int levels_for(int H, int W) {
   int L = 1;
   while ((kTile << (2 * (L - 1))) < (H > W ? H : W)) ++L;
@@ -788,25 +893,40 @@ int bins_per_view(int H, int W) {
   return nb;
 }
 
-size_t workspace_bytes(int B, int64_t NF, int H, int W) {
-  const size_t cnt = align_up((size_t)2 * B * bins_per_view(H, W) * sizeof(int), 256);
-  const size_t ent = align_up((size_t)2 * 4 * (size_t)(NF > 0 ? NF : 1) * sizeof(int4), 256);
-  return 2 * cnt + ent + 256;
+// Workspace layout (all pieces 256-byte aligned):
+//   cnt [2*B*NB] int + pool_ctr | off [2*B*NB] int | tile_mode [tiles] u8 |
+//   entries [2*4*NF] int4 | pool_hdr [pool_tiles] int4 | pool_data [pool_tiles][3][256*K] u32
+struct Layout { size_t cnt, off, mode, ent, base; };
+
+Layout layout_for(int B, int64_t NF, int H, int W) {
+  Layout L;
+  const size_t tiles = (size_t)((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile) * B;
+  L.cnt = align_up(((size_t)2 * B * bins_per_view(H, W) + 1) * sizeof(int), 256);
+  L.off = align_up((size_t)2 * B * bins_per_view(H, W) * sizeof(int), 256);
+  L.mode = align_up(tiles, 256);
+  L.ent = align_up((size_t)2 * 4 * (size_t)(NF > 0 ? NF : 1) * sizeof(int4), 256);
+  L.base = L.cnt + L.off + L.mode + L.ent + 256;
+  return L;
 }
+
+size_t pool_block_bytes(int K) { return sizeof(int4) + (size_t)3 * 256 * (size_t)K * sizeof(uint32_t); }
 
 int check_dims(int B, int64_t NF, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0 || NF < 0) return DIBR_B200_EINVAL;
-  if (H > DIBR_B200_MAX_IMAGE_DIM || W > DIBR_B200_MAX_IMAGE_DIM) return DIBR_B200_ESIZE;
-  const int64_t tiles = (int64_t)((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile) * B;
-  if (tiles > 0x7fffffffLL || NF > 0x3fffffffLL) return DIBR_B200_ESIZE;
+  if (H > DIBR_B200_MAX_IMAGE_DIM || W > DIBR_B200_MAX_IMAGE_DIM || B > 65535) return DIBR_B200_ESIZE;
+  if (NF > 0x3fffffffLL) return DIBR_B200_ESIZE;
   return 0;
 }
 
+// knum > 0 enables the hit cache in whatever the workspace holds beyond the minimum.
 int setup_scene(Scene& s, int B, int64_t NF, int F, int H, int W, float multiplier, float margin,
-                void* ws, size_t ws_bytes) {
+                int knum, void* ws, size_t ws_bytes) {
   if (!(multiplier > 0.f)) return DIBR_B200_EINVAL;
-  if (!ws || ((uintptr_t)ws & 15)) return DIBR_B200_EINVAL;
-  if (ws_bytes < workspace_bytes(B, NF, H, W)) return DIBR_B200_EWORKSPACE;
+  if (!ws) return DIBR_B200_EINVAL;
+  const Layout Lo = layout_for(B, NF, H, W);
+  char* p = (char*)align_up((size_t)ws, 256);
+  char* const end = (char*)ws + ws_bytes;
+  if (ws_bytes < Lo.base || p + Lo.cnt + Lo.off + Lo.mode + Lo.ent > end) return DIBR_B200_EWORKSPACE;
   s.B = B; s.H = H; s.W = W; s.F = F; s.NF = NF;
   s.multiplier = multiplier; s.margin = margin;
   s.grid = make_grid(multiplier, W, H);
@@ -820,17 +940,31 @@ int setup_scene(Scene& s, int B, int64_t NF, int F, int H, int W, float multipli
     nb += s.ntx[l] * s.nty[l];
   }
   s.NB = nb;
-  char* p = (char*)ws;
-  p = (char*)align_up((size_t)p, 256);
-  const size_t cnt = align_up((size_t)2 * B * nb * sizeof(int), 256);
-  s.cnt = (int*)p; p += cnt;
-  s.off = (int*)p; p += cnt;
-  s.entries = (int4*)p;
+  s.cnt = (int*)p;
+  s.pool_ctr = s.cnt + (size_t)2 * B * nb;
+  p += Lo.cnt;
+  s.off = (int*)p; p += Lo.off;
+  s.tile_mode = (uint8_t*)p; p += Lo.mode;
+  s.entries = (int4*)p; p += Lo.ent;
+  s.pool_tiles = 0; s.pool_K = knum > 0 ? knum : 1; s.pool_hdr = nullptr; s.pool_data = nullptr;
+  if (knum > 0) {
+    const size_t left = (size_t)(end - p);
+    const size_t data = (size_t)3 * 256 * (size_t)knum * sizeof(uint32_t);
+    size_t n = left / (data + sizeof(int4));
+    const size_t tiles = (size_t)s.ntx[0] * s.nty[0] * B;
+    if (n > tiles) n = tiles;
+    while (n > 0 && align_up(n * sizeof(int4), 256) + n * data > left) --n;
+    if (n > 0) {
+      s.pool_tiles = (int)n;
+      s.pool_hdr = (int4*)p;
+      s.pool_data = (uint32_t*)(p + align_up(n * sizeof(int4), 256));
+    }
+  }
   return 0;
 }
 
 int build_bins(const Scene& s, int sets, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(s.cnt, 0, (size_t)2 * s.B * s.NB * sizeof(int), st);
+  cudaError_t e = cudaMemsetAsync(s.cnt, 0, ((size_t)2 * s.B * s.NB + 1) * sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
   if (s.NF > 0) {
     const unsigned blocks = (unsigned)((s.NF + 255) / 256);
@@ -841,20 +975,21 @@ int build_bins(const Scene& s, int sets, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
+dim3 tile_grid(const Scene& s) { return dim3((unsigned)s.ntx[0], (unsigned)s.nty[0], (unsigned)s.B); }
+
 template <bool R, bool S, bool K>
 void launch_fwd(const FwdArgs& a, cudaStream_t st) {
-  const unsigned tiles = (unsigned)(a.s.ntx[0] * a.s.nty[0] * a.s.B);
-  dibr_tile_fwd_kernel<R, S, K><<<tiles, kThreads, 0, st>>>(a);
+  dibr_tile_fwd_kernel<R, S, K><<<tile_grid(a.s), kThreads, 0, st>>>(a);
 }
 
 int launch_raster_bwd(const RasterBwdArgs& a, cudaStream_t st) {
-  const unsigned tiles = (unsigned)(a.ntx * a.nty * a.B);
+  const dim3 grid((unsigned)a.ntx, (unsigned)a.nty, (unsigned)a.B);
   switch (a.D) {
-    case 1: raster_bwd_kernel<1><<<tiles, kThreads, 0, st>>>(a); break;
-    case 2: raster_bwd_kernel<2><<<tiles, kThreads, 0, st>>>(a); break;
-    case 3: raster_bwd_kernel<3><<<tiles, kThreads, 0, st>>>(a); break;
-    case 4: raster_bwd_kernel<4><<<tiles, kThreads, 0, st>>>(a); break;
-    default: raster_bwd_kernel<0><<<tiles, kThreads, 0, st>>>(a); break;
+    case 1: raster_bwd_kernel<1><<<grid, kThreads, 0, st>>>(a); break;
+    case 2: raster_bwd_kernel<2><<<grid, kThreads, 0, st>>>(a); break;
+    case 3: raster_bwd_kernel<3><<<grid, kThreads, 0, st>>>(a); break;
+    case 4: raster_bwd_kernel<4><<<grid, kThreads, 0, st>>>(a); break;
+    default: raster_bwd_kernel<0><<<grid, kThreads, 0, st>>>(a); break;
   }
   return (int)cudaGetLastError();
 }
@@ -868,7 +1003,16 @@ int dibr_b200_version(void) { return 100; }
 
 size_t dibr_b200_workspace_bytes(int batch, int64_t total_faces, int height, int width) {
   if (check_dims(batch, total_faces, height, width)) return 0;
-  return workspace_bytes(batch, total_faces, height, width);
+  return layout_for(batch, total_faces, height, width).base;
+}
+
+size_t dibr_b200_workspace_bytes_cached(int batch, int64_t total_faces, int height, int width,
+                                        int knum, int64_t cache_tiles) {
+  if (check_dims(batch, total_faces, height, width) || knum <= 0 || cache_tiles < 0) return 0;
+  const int64_t tiles = (int64_t)((width + kTile - 1) / kTile) * ((height + kTile - 1) / kTile) * batch;
+  if (cache_tiles > tiles) cache_tiles = tiles;
+  return layout_for(batch, total_faces, height, width).base + 512 +
+         (size_t)cache_tiles * pool_block_bytes(knum);
 }
 
 int dibr_b200_forward(int batch, int num_faces, int height, int width, int feat_dim,
@@ -891,7 +1035,8 @@ int dibr_b200_forward(int batch, int num_faces, int height, int width, int feat_
   cudaStream_t st = (cudaStream_t)stream;
   FwdArgs a;
   Scene& s = a.s;
-  rc = setup_scene(s, batch, NF, num_faces, height, width, multiplier, boxlen_m, workspace, workspace_bytes_);
+  rc = setup_scene(s, batch, NF, num_faces, height, width, multiplier, boxlen_m, soft ? knum : 0,
+                   workspace, workspace_bytes_);
   if (rc) return rc;
   s.first = nullptr; s.xy = face_vertices_image; s.z = face_vertices_z; s.premultiplied = 0;
   s.fnz = face_normals_z; s.valid = valid_faces; s.bbox_tight = nullptr; s.bbox_large = nullptr;
@@ -899,6 +1044,7 @@ int dibr_b200_forward(int batch, int num_faces, int height, int width, int feat_
   if (rc) return rc;
   a.rc = make_raster_const(eps);
   a.D = feat_dim; a.feat = face_features; a.sigmainv = sigmainv; a.K = knum;
+  a.cache = soft ? 1 : 0;   // tile_mode is always written; hits are cached while blocks last
   a.out_feat = interpolated_features; a.idx = face_idx; a.out_w = output_weights; a.out_soft = soft_mask;
   a.kl = SoftFwdOut{nullptr, nullptr, nullptr};
   if (raster && soft) launch_fwd<true, true, false>(a, st);
@@ -941,19 +1087,26 @@ int dibr_b200_backward(int batch, int num_faces, int height, int width, int feat
   if (grad_soft_mask) {
     if (!soft_mask || knum <= 0) return DIBR_B200_EINVAL;
     SoftBwdArgs a;
-    rc = setup_scene(a.s, batch, NF, num_faces, height, width, multiplier, boxlen_m, workspace, workspace_bytes_);
+    rc = setup_scene(a.s, batch, NF, num_faces, height, width, multiplier, boxlen_m, knum, workspace,
+                     workspace_bytes_);
     if (rc) return rc;
     Scene& s = a.s;
     s.first = nullptr; s.xy = face_vertices_image; s.z = nullptr; s.premultiplied = 0;
     s.fnz = nullptr; s.valid = nullptr; s.bbox_tight = nullptr; s.bbox_large = nullptr;
-    if (!bins_valid) {
-      rc = build_bins(s, 2, st);
-      if (rc) return rc;
-    }
     a.sigmainv = sigmainv; a.K = knum; a.grad_soft = grad_soft_mask; a.soft = soft_mask;
     a.idx = face_idx; a.grad_xy = grad_face_vertices_image;
-    const unsigned tiles = (unsigned)(s.ntx[0] * s.nty[0] * s.B);
-    dibr_tile_soft_bwd_kernel<<<tiles, kThreads, 0, st>>>(a);
+    if (!bins_valid) {
+      // no forward state: rebuild the large bins and recompute every tile
+      rc = build_bins(s, 2, st);
+      if (rc) return rc;
+      a.only_mode2 = 0;
+      dibr_tile_soft_bwd_kernel<<<tile_grid(s), kThreads, 0, st>>>(a);
+    } else {
+      // forward left bins + tile_mode + the hit cache in the workspace
+      a.only_mode2 = 1;
+      if (s.pool_tiles > 0) soft_bwd_dense_kernel<<<(unsigned)s.pool_tiles, kThreads, 0, st>>>(a);
+      dibr_tile_soft_bwd_kernel<<<tile_grid(s), kThreads, 0, st>>>(a);
+    }
     return (int)cudaGetLastError();
   }
   return 0;
@@ -976,7 +1129,7 @@ int dibr_b200_packed_rasterize_forward(int batch, int64_t total_faces, int heigh
   cudaStream_t st = (cudaStream_t)stream;
   FwdArgs a;
   Scene& s = a.s;
-  rc = setup_scene(s, batch, total_faces, 0, height, width, multiplier, 0.f, workspace, workspace_bytes_);
+  rc = setup_scene(s, batch, total_faces, 0, height, width, multiplier, 0.f, 0, workspace, workspace_bytes_);
   if (rc) return rc;
   s.first = first_idx_face_per_mesh; s.xy = face_vertices_image; s.z = face_vertices_z;
   s.premultiplied = 1; s.fnz = nullptr; s.valid = nullptr; s.bbox_tight = face_bboxes; s.bbox_large = nullptr;
@@ -985,6 +1138,7 @@ int dibr_b200_packed_rasterize_forward(int batch, int64_t total_faces, int heigh
   a.rc = make_raster_const(eps);
   a.D = feat_dim; a.feat = face_features; a.sigmainv = 0.f; a.K = 0;
   a.out_feat = interpolated_features; a.idx = selected_face_idx; a.out_w = output_weights; a.out_soft = nullptr;
+  a.cache = 0;
   a.kl = SoftFwdOut{nullptr, nullptr, nullptr};
   launch_fwd<true, false, false>(a, st);
   return (int)cudaGetLastError();
@@ -1021,7 +1175,7 @@ int dibr_b200_soft_mask_forward(int batch, int num_faces, int height, int width,
   cudaStream_t st = (cudaStream_t)stream;
   FwdArgs a;
   Scene& s = a.s;
-  rc = setup_scene(s, batch, NF, num_faces, height, width, multiplier, 0.f, workspace, workspace_bytes_);
+  rc = setup_scene(s, batch, NF, num_faces, height, width, multiplier, 0.f, 0, workspace, workspace_bytes_);
   if (rc) return rc;
   s.first = nullptr; s.xy = face_vertices_image; s.z = nullptr; s.premultiplied = 1;
   s.fnz = nullptr; s.valid = nullptr; s.bbox_tight = nullptr; s.bbox_large = face_large_bboxes;
@@ -1030,6 +1184,7 @@ int dibr_b200_soft_mask_forward(int batch, int num_faces, int height, int width,
   a.rc = make_raster_const(0.f);
   a.D = 0; a.feat = nullptr; a.sigmainv = sigmainv; a.K = knum;
   a.out_feat = nullptr; a.idx = const_cast<int64_t*>(selected_face_idx); a.out_w = nullptr; a.out_soft = soft_mask;
+  a.cache = 0;
   a.kl = SoftFwdOut{close_face_prob, close_face_idx, close_face_dist_type};
   if (lists) launch_fwd<false, true, true>(a, st);
   else launch_fwd<false, true, false>(a, st);

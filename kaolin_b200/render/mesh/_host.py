@@ -42,8 +42,21 @@ def check_size(func, name, t, shape):
         raise RuntimeError(f"{func}: expected {name} of size {list(shape)}, got {list(t.shape)}")
 
 
-def workspace(batch, total_faces, height, width, device):
-    n = _lib.lib().dibr_b200_workspace_bytes(batch, total_faces, height, width)
+# fraction of the screen tiles whose soft-mask hits are cached for backward (the
+# silhouette band is a few percent of the image; tiles beyond the cache are recomputed)
+CACHE_TILE_FRACTION = 0.125
+CACHE_MIN_TILES = 64
+CACHE_MAX_BYTES = 4 << 30
+
+
+def workspace(batch, total_faces, height, width, device, knum=0):
+    if knum > 0:
+        tiles = batch * ((height + 15) // 16) * ((width + 15) // 16)
+        want = max(CACHE_MIN_TILES, int(tiles * CACHE_TILE_FRACTION))
+        want = min(tiles, want, max(1, CACHE_MAX_BYTES // (3072 * knum + 16)))
+        n = _lib.lib().dibr_b200_workspace_bytes_cached(batch, total_faces, height, width, knum, want)
+    else:
+        n = _lib.lib().dibr_b200_workspace_bytes(batch, total_faces, height, width)
     if n == 0:
         raise RuntimeError("kaolin_b200: unsupported problem size "
                            f"(batch={batch}, faces={total_faces}, image={height}x{width})")
@@ -62,7 +75,7 @@ def forward(mode, height, width, fvz, fvi, ff, fnz, valid_u8, multiplier, eps,
     wts = torch.empty((B, height, width, 3), dtype=torch.float32, device=dev) if raster else None
     idx = torch.empty((B, height, width), dtype=torch.int64, device=dev) if raster else face_idx_in
     soft = torch.empty((B, height, width), dtype=torch.float32, device=dev) if soft_on else None
-    ws = workspace(B, B * F, height, width, dev)
+    ws = workspace(B, B * F, height, width, dev, knum if soft_on else 0)
     with torch.cuda.device(dev):
         st = _lib.lib().dibr_b200_forward(
             B, F, height, width, D, ptr(fvz), ptr(fvi), ptr(ff), ptr(fnz), ptr(valid_u8),

@@ -186,58 +186,52 @@ void oracle_rasterize_backward_rows(
         acc_ff[start_features_idx + ii * D + d] += (double)val;
       }
     }
-    /* :292-374 */
+    /* :292-374 — expression tree as compiled by nvcc 12.9 for the <float> kernel
+     * (SASS offsets 0x20b0-0x27d0 of oracle/_ref/rasterization_cuda.cu.o).  The
+     * partials are differences of nearly equal products divided by k3^2, so a
+     * different (mathematically equal) association differs by ~1e-4 relative. */
     const float* p = face_vertices_image + start_image_idx;
     const float ax = p[0], ay = p[1], bx = p[2], by = p[3], cx = p[4], cy = p[5];
     const float aw = wv[0], bw = wv[1], cw = wv[2];
-    const float x0 = aw * ax + bw * bx + cw * cx;
-    const float y0 = aw * ay + bw * by + cw * cy;
-    const float m = bx - ax, pp = by - ay;
-    const float n = cx - ax, q = cy - ay;
-    const float s = x0 - ax, t = y0 - ay;
-    const float k1 = s * q - n * t;
-    const float k2 = m * t - s * pp;
-    float k3 = m * q - n * pp;
+    const float pp = by - ay, n = cx - ax, m = bx - ax, q = cy - ay;
+    float k3 = fmaf(m, q, -(pp * n));
     k3 = (float)((double)k3 + copysign((double)eps, (double)k3));
-
-    const float dk1dm = 0, dk1dn = -t, dk1dp = 0, dk1dq = s, dk1ds = q, dk1dt = -n;
-    const float dk2dm = t, dk2dn = 0, dk2dp = -s, dk2dq = 0, dk2ds = -pp, dk2dt = m;
-    const float dk3dm = q, dk3dn = -pp, dk3dp = -n, dk3dq = m, dk3ds = 0, dk3dt = 0;
-
-    const float dw1dm = dk1dm * k3 - dk3dm * k1;
-    const float dw1dn = dk1dn * k3 - dk3dn * k1;
-    const float dw1dp = dk1dp * k3 - dk3dp * k1;
-    const float dw1dq = dk1dq * k3 - dk3dq * k1;
-    const float dw1ds = dk1ds * k3 - dk3ds * k1;
-    const float dw1dt = dk1dt * k3 - dk3dt * k1;
-
-    const float dw2dm = dk2dm * k3 - dk3dm * k2;
-    const float dw2dn = dk2dn * k3 - dk3dn * k2;
-    const float dw2dp = dk2dp * k3 - dk3dp * k2;
-    const float dw2dq = dk2dq * k3 - dk3dq * k2;
-    const float dw2ds = dk2ds * k3 - dk3ds * k2;
-    const float dw2dt = dk2dt * k3 - dk3dt * k2;
-
-    const float dw1dax = -(dw1dm + dw1dn + dw1ds);
-    const float dw1day = -(dw1dp + dw1dq + dw1dt);
-    const float dw1dbx = dw1dm, dw1dby = dw1dp, dw1dcx = dw1dn, dw1dcy = dw1dq;
-    const float dw2dax = -(dw2dm + dw2dn + dw2ds);
-    const float dw2day = -(dw2dp + dw2dq + dw2dt);
-    const float dw2dbx = dw2dm, dw2dby = dw2dp, dw2dcx = dw2dn, dw2dcy = dw2dq;
+    const float y0 = fmaf(cy, cw, fmaf(ay, aw, by * bw));
+    const float x0 = fmaf(cx, cw, fmaf(ax, aw, bx * bw));
+    const float t = y0 - ay, s = x0 - ax;
+    const float k1 = fmaf(q, s, -(n * t));
+    const float k2 = fmaf(m, t, -(pp * s));
+    const float z1 = 0.f * k1, z3 = 0.f * k3, z2 = 0.f * k2;
+    const float tk3 = t * k3, sk3 = s * k3;
+    const float dw1ds = fmaf(q, k3, -z1);     /* dk1ds*k3 - dk3ds*k1 */
+    const float dw1dm = fmaf(-q, k1, z3);     /* dk1dm*k3 - dk3dm*k1 */
+    const float dw2dm = fmaf(-q, k2, tk3);
+    const float dw1dn = fmaf(pp, k1, -tk3);
+    const float dw1dp = fmaf(n, k1, z3);
+    const float dw1dq = fmaf(-m, k1, sk3);
+    const float dw1dt = fmaf(-n, k3, -z1);
+    const float dw2dp = fmaf(n, k2, -sk3);
+    const float dw2ds = fmaf(-pp, k3, -z2);
+    const float dw2dt = fmaf(m, k3, -z2);
+    const float dw2dn = fmaf(pp, k2, z3);
+    const float dw2dq = fmaf(-m, k2, z3);
+    /* :362-374; the a-vertex partials are kept negated, as the compiled code does */
+    const float n1ay = dw1dt + (dw1dp + dw1dq);
+    const float n1ax = dw1ds + (dw1dm + dw1dn);
+    const float n2ax = dw2ds + (dw2dm + dw2dn);
+    const float n2ay = dw2dt + (dw2dp + dw2dq);
+    const float k3sq = k3 * k3;
 
     const float* ff = face_features + start_features_idx;
     /* :376-399 */
     for (int d = 0; d < D; d++) {
       const float c0 = ff[d], c1 = ff[D + d], c2 = ff[2 * D + d];
-      const float dIdax = (c1 - c0) * dw1dax + (c2 - c0) * dw2dax;
-      const float dIday = (c1 - c0) * dw1day + (c2 - c0) * dw2day;
-      const float dIdbx = (c1 - c0) * dw1dbx + (c2 - c0) * dw2dbx;
-      const float dIdby = (c1 - c0) * dw1dby + (c2 - c0) * dw2dby;
-      const float dIdcx = (c1 - c0) * dw1dcx + (c2 - c0) * dw2dcx;
-      const float dIdcy = (c1 - c0) * dw1dcy + (c2 - c0) * dw2dcy;
-      const float dldI = g[d] / (k3 * k3);
-      const float v[6] = {dldI * dIdax, dldI * dIday, dldI * dIdbx,
-                          dldI * dIdby, dldI * dIdcx, dldI * dIdcy};
+      const float d1 = c1 - c0, d2 = c2 - c0;
+      const float dldI = g[d] / k3sq;
+      const float v[6] = {
+          fmaf(-n2ax, d2, -(n1ax * d1)) * dldI, fmaf(-n2ay, d2, -(n1ay * d1)) * dldI,
+          fmaf(dw1dm, d1, dw2dm * d2) * dldI,   fmaf(dw1dp, d1, dw2dp * d2) * dldI,
+          fmaf(dw1dn, d1, dw2dn * d2) * dldI,   fmaf(dw1dq, d1, dw2dq * d2) * dldI};
       for (int j = 0; j < 6; j++) {
 #pragma omp atomic
         acc_xy[start_image_idx + j] += (double)v[j];
@@ -411,22 +405,26 @@ void oracle_soft_mask_backward_rows(
         acc[pshift] += (double)(dLdx1 / multiplier);
 #pragma omp atomic
         acc[pshift + 1] += (double)(dLdy1 / multiplier);
-      } else { /* :304-347 */
+      } else { /* :304-347, with the FMA contraction of the compiled <float> kernel */
         const int64_t pshift = shift6 + edgeid * 2;
         const int64_t pshift2 = shift6 + ((edgeid + 1) % 3) * 2;
         const float x1 = face_vertices_image[pshift], y1 = face_vertices_image[pshift + 1];
         const float x2 = face_vertices_image[pshift2], y2 = face_vertices_image[pshift2 + 1];
-        const float A = y2 - y1, Bc = x1 - x2, C = x2 * y1 - x1 * y2;
-        const float up = A * x0 + Bc * y0 + C;
-        const float down = A * A + Bc * Bc;
-        const float dissquare = (float)(up * up / (down + SOFT_EPS));
-        const float dzdA = (float)(2 * (x0 * up - dissquare * A) / (down + SOFT_EPS));
-        const float dzdB = (float)(2 * (y0 * up - dissquare * Bc) / (down + SOFT_EPS));
-        const float dzdC = (float)(2 * up / (down + SOFT_EPS));
-        const float dLdx1 = dLdz * (dzdB - y2 * dzdC);
-        const float dLdy1 = dLdz * (x2 * dzdC - dzdA);
-        const float dLdx2 = dLdz * (y1 * dzdC - dzdB);
-        const float dLdy2 = dLdz * (dzdA - x1 * dzdC);
+        const float A = y2 - y1, Bc = x1 - x2;
+        const float C = fmaf(y1, x2, -(x1 * y2));
+        const float up = C + fmaf(y0, Bc, x0 * A);
+        const float down = fmaf(Bc, Bc, A * A);
+        const double down64 = (double)down + SOFT_EPS;
+        const float dissquare = (float)((double)(up * up) / down64);
+        const float nA = fmaf(x0, up, -(A * dissquare));
+        const float nB = fmaf(y0, up, -(Bc * dissquare));
+        const float dzdA = (float)((double)(nA + nA) / down64);
+        const float dzdB = (float)((double)(nB + nB) / down64);
+        const float dzdC = (float)((double)(up + up) / down64);
+        const float dLdx1 = dLdz * fmaf(-y2, dzdC, dzdB);
+        const float dLdy1 = dLdz * fmaf(x2, dzdC, -dzdA);
+        const float dLdx2 = dLdz * fmaf(y1, dzdC, -dzdB);
+        const float dLdy2 = dLdz * fmaf(-x1, dzdC, dzdA);
 #pragma omp atomic
         acc[pshift] += (double)(dLdx1 / multiplier);
 #pragma omp atomic

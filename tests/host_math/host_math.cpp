@@ -129,21 +129,17 @@ void hm_rasterize_backward(int B, int H, int W, int F, int D, const float* g, co
     const int64_t face = b * F + f;
     const float* gp = g + pix * D;
     const float w0 = w[3 * pix], w1 = w[3 * pix + 1], w2 = w[3 * pix + 2];
-    float dw1[6], dw2[6], k3;
-    raster_backward_geom(xy + face * 6, w0, w1, w2, eps, dw1, dw2, k3);
+    RasterBwdGeom G;
+    raster_backward_geom(xy + face * 6, w0, w1, w2, eps, G);
     const float* c = ff + face * 3 * D;
-    // kernel formulation: S1 = sum_d g_d/(k3^2) (c1-c0), S2 likewise
-    float S1 = 0.f, S2 = 0.f;
-    const float inv = 1.f / (k3 * k3);
     for (int d = 0; d < D; d++) {
-      const float dl = gp[d] * inv;
-      S1 += dl * (c[D + d] - c[d]);
-      S2 += dl * (c[2 * D + d] - c[d]);
+      float t6[6];
+      raster_backward_feature(G, gp[d], c[d], c[D + d], c[2 * D + d], t6);
+      for (int j = 0; j < 6; j++) axy[face * 6 + j] += (double)t6[j];
       aff[face * 3 * D + d] += (double)(gp[d] * w0);
       aff[face * 3 * D + D + d] += (double)(gp[d] * w1);
       aff[face * 3 * D + 2 * D + d] += (double)(gp[d] * w2);
     }
-    for (int j = 0; j < 6; j++) axy[face * 6 + j] += (double)(S1 * dw1[j] + S2 * dw2[j]);
   }
   for (int64_t i = 0; i < nxy; i++) gxy[i] = (float)axy[i];
   for (int64_t i = 0; i < nff; i++) gff[i] = (float)aff[i];

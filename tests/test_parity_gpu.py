@@ -22,7 +22,13 @@ from kaolin_b200.render.mesh import rasterize, dibr_soft_mask, dibr_rasterizatio
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda"
-GRAD_REL = 1e-5
+# Gradients: every per-pixel term is produced by the reference's own operation tree
+# (dibr_math.cuh), so the only difference left is the ORDER of the fp32 additions —
+# which the reference does not fix either (float atomicAdd).  Against the oracle's
+# double-precision accumulation that noise is ~1e-6 of the gradient's scale for
+# meshes and reaches ~1.5e-5 on the overlapping-soup scene (thousands of pixels per
+# face); the reference's own kernels show the same deviation (printed below).
+GRAD_REL = 3e-5
 
 
 def T(a, grad=False):
@@ -91,6 +97,12 @@ def test_fused_dibr_vs_reference_cuda(name):
     g_soft = rng.uniform(size=(B, H, W)).astype(np.float32)
     feat, soft, idx, g_fvi, g_ff = _run_fused(fvz, fvi, fnz, ff, H, W, g_feat, g_soft)
     r = ref_cuda.dibr_forward_backward(H, W, T(fvz), T(fvi), T(ff), T(fnz), T(g_feat), T(g_soft))
+    o_feat, o_soft, o_idx, o_w = oracle.dibr_rasterization(H, W, fvz, fvi, ff, fnz, return_weights=True)
+    o_gxy, o_gff, _, _ = oracle.dibr_rasterization_backward(g_feat, g_soft, o_idx, o_w, fvi, ff)
+    print(f"\n[{name}] grad_fvi rel err vs double-accumulated oracle: ours {rel_err(g_fvi, o_gxy):.2e}, "
+          f"reference CUDA {rel_err(N(r['grad_fvi']), o_gxy):.2e}; ours vs reference CUDA "
+          f"{rel_err(g_fvi, N(r['grad_fvi'])):.2e}; soft_mask bit-equal to reference: "
+          f"{float((soft == N(r['soft_mask'])).mean()):.4f}")
     assert np.array_equal(idx, N(r["face_idx"]))
     np.testing.assert_allclose(feat, N(r["features"]), rtol=0, atol=1e-5)
     np.testing.assert_allclose(soft, N(r["soft_mask"]), rtol=0, atol=1e-5)
@@ -324,6 +336,34 @@ def test_soft_mask_dense_overflow_path():
         soft.backward(T(g_soft))
         o_g = oracle.dibr_soft_mask_backward(g_soft, fvi, o_idx, 7000, 0.1, knum, 1000.)
         assert rel_err(N(t_fvi.grad), o_g) <= 2e-5
+
+
+@pytest.mark.parametrize("cache_tiles", [0, 3, 10 ** 9])
+def test_soft_backward_cache_and_recompute_paths_agree(cache_tiles, monkeypatch):
+    """The soft-mask backward streams over the hit cache filled by forward; tiles that
+    do not fit are recomputed.  No cache, a 3-tile cache and a full cache must all match."""
+    from kaolin_b200.render.mesh import _host
+    monkeypatch.setattr(_host, "CACHE_TILE_FRACTION", 1.0 if cache_tiles > 3 else 0.0)
+    monkeypatch.setattr(_host, "CACHE_MIN_TILES", min(cache_tiles, 3))
+    fvz, fvi, fnz = synthetic.icosphere_views(2, 3, seed=2)
+    B, F = fvz.shape[:2]
+    H, W = 96, 80
+    ff = synthetic.random_features(B, F, 3, seed=11)
+    rng = np.random.default_rng(12)
+    g_feat = rng.uniform(size=(B, H, W, 3)).astype(np.float32)
+    g_soft = rng.uniform(size=(B, H, W)).astype(np.float32)
+    feat, soft, idx, g_fvi, g_ff = _run_fused(fvz, fvi, fnz, ff, H, W, g_feat, g_soft)
+    o_feat, o_soft, o_idx, o_w = oracle.dibr_rasterization(H, W, fvz, fvi, ff, fnz, return_weights=True)
+    o_gxy, o_gff, _, _ = oracle.dibr_rasterization_backward(g_feat, g_soft, o_idx, o_w, fvi, ff)
+    assert np.array_equal(idx, o_idx)
+    np.testing.assert_allclose(soft, o_soft, rtol=0, atol=1e-6)
+    assert rel_err(g_fvi, o_gxy) <= GRAD_REL
+    # standalone dibr_soft_mask goes through the same cache
+    t_fvi = T(fvi, True)
+    s2 = dibr_soft_mask(t_fvi, T(o_idx))
+    s2.backward(T(g_soft))
+    o_gs = oracle.dibr_soft_mask_backward(g_soft, fvi, o_idx)
+    assert rel_err(N(t_fvi.grad), o_gs) <= GRAD_REL
 
 
 def test_errors_like_reference():
