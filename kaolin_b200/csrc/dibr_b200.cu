@@ -33,6 +33,8 @@ constexpr int kThreads = 256;
 constexpr int kChunk = 256;
 constexpr int kMaxLevels = 6;   // 16 * 4^5 = 16384 px
 constexpr int kSoftCap = 1024;  // soft-mask candidates sorted per pass
+constexpr int kRound = 16;      // hits a pixel contributes to one pair round
+constexpr int kPairCap = kThreads * kRound;
 constexpr unsigned kFull = 0xffffffffu;
 
 // ---------------------------------------------------------------------------
@@ -64,7 +66,10 @@ struct Scene {
   int* pool_ctr;          // [1] blocks handed out
   int4* pool_hdr;         // [pool_tiles] {b, tx, ty, hits}
   uint32_t* pool_data;    // [pool_tiles][3][256*K]: face | prob bits | lx|ly<<4|(dist_type)<<8
-  uint8_t* tile_mode;     // [B*nty*ntx] 0: no soft work, 1: hits cached, 2: recompute in backward
+  int* fb_ctr;            // [1] tiles whose hits did not fit the cache (recomputed in backward)
+  int* fb_list;           // [B*nty*ntx] their linear tile ids
+  int* band_ctr;          // [1] tiles with uncovered pixels under some enlarged face rectangle
+  int* band_list;         // [B*nty*ntx] their linear tile ids (work list of the soft-mask kernel)
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -307,14 +312,49 @@ struct TileSmem {
   float acc[kChunk][6];                  // soft-mask backward per-candidate sums
   unsigned long long bar[2];
   BinRef bin[2][kMaxLevels];             // the tile's bins (set, level): filled once by warp 0
+  uint8_t apix[kThreads];                // compacted uncovered pixels of the tile: lx | ly << 4
+  int wcount[kThreads / 32];
   int ncand;
   int nsoft;
   int nent;                              // hits appended to the cache block
   int pool_slot;                         // cache block of this tile (-1: none)
+  int npairs;                            // (pixel, face) pairs of the current round
 };
 
+// Shared memory of the rasterizing tile kernel (a subset: 4-5 CTAs more per SM).
+struct RasterSmem {
+  int4 stage[2][kChunk];
+  float4 cxy0[kChunk];
+  float4 cz[kChunk];
+  float2 cxy1[kChunk];
+  int cface[kChunk];
+  uint32_t colbits[kChunk / 32][16];     // [group of 32 candidates][tile column] -> candidate bits
+  uint32_t rowbits[kChunk / 32][16];     // [group][tile row]
+  unsigned long long bar[2];
+  BinRef bin[2][kMaxLevels];
+};
+
+// Transposes the tile-local rectangle masks of the 32 candidates held by a warp
+// (one per lane) into per-column / per-row candidate bit words: a pixel (lx, ly)
+// is inside candidate j's rectangle  <=>  bit j of colbits[g][lx] & rowbits[g][ly].
+// Every pixel then walks exactly its own rectangle hits (ffs), lane-privately.
+__device__ __forceinline__ void store_bit_matrix(uint32_t m, uint32_t (*colbits)[16], uint32_t (*rowbits)[16],
+                                                 int g) {
+  const int lane = threadIdx.x & 31;
+  uint32_t mine = 0;
+  if (__any_sync(kFull, m != 0)) {
+#pragma unroll
+    for (int b = 0; b < 32; ++b) {
+      const uint32_t r = __ballot_sync(kFull, (m >> b) & 1u);
+      if (lane == b) mine = r;
+    }
+  }
+  if (lane < 16) colbits[g][lane] = mine; else rowbits[g][lane - 16] = mine;
+}
+
 // Lanes 0..L-1 / 8..8+L-1 of warp 0 look up the tight / large bins of the tile.
-__device__ __forceinline__ void load_bin_table(const Scene& s, const TileCtx& c, TileSmem& sm) {
+template <typename SM>
+__device__ __forceinline__ void load_bin_table(const Scene& s, const TileCtx& c, SM& sm) {
   const int tid = threadIdx.x;
   if (tid < 16) {
     const int set = tid >> 3, l = tid & 7;
@@ -330,9 +370,10 @@ __device__ __forceinline__ void load_bin_table(const Scene& s, const TileCtx& c,
 // Rasterization of one tile: walks the "tight" bins of every level.
 struct RasterOut { float z, w0, w1, w2; int f; };
 
+template <typename SM>
 __device__ __forceinline__ void raster_tile(const Scene& s, const TileCtx& c, const RasterConst& rc,
-                                            TileSmem& sm, RasterOut& o) {
-  const int tid = threadIdx.x, lane = tid & 31;
+                                            SM& sm, RasterOut& o) {
+  const int tid = threadIdx.x;
   o.z = -INFINITY; o.f = -1; o.w0 = o.w1 = o.w2 = 0.f;
 
   // The (<= 6) tight bins above the tile form one virtual list, streamed in
@@ -359,46 +400,44 @@ __device__ __forceinline__ void raster_tile(const Scene& s, const TileCtx& c, co
 
   if (tid == 0) issue(0);
   for (int k = 0; k < nrounds; ++k) {
-    if (tid == 0) {
-      sm.ncand = 0;
-      if (k + 1 < nrounds) issue(k + 1);  // buffer (k+1)&1 was released by the sync ending round k-1
-    }
-    __syncthreads();
+    if (tid == 0 && k + 1 < nrounds) issue(k + 1);  // buffer (k+1)&1 was released by the sync ending round k-1
     const int cnt = min(kChunk, total - k * kChunk);
     mbar_wait(&sm.bar[k & 1], (uint32_t)((k >> 1) & 1));
 
-    // cull against the tile, gather the face, stage the record
-    uint32_t m = 0; int4 e = make_int4(0, 0, 0, 0);
-    if (tid < cnt) { e = sm.stage[k & 1][tid]; m = tile_mask(e, c.tile_x0, c.tile_y0); }
-    const unsigned vote = __ballot_sync(kFull, m != 0);
-    int base = 0;
-    if (lane == 0 && vote) base = atomicAdd(&sm.ncand, __popc(vote));
-    base = __shfl_sync(kFull, base, 0);
-    if (m) {
-      const int slot = base + __popc(vote & ((1u << lane) - 1u));
-      const int64_t g = c.fbase + e.x;
-      float v[6];
-      load_xy(s, g, v);
-      const float* zp = s.z + g * 3;
-      sm.cxy0[slot] = make_float4(v[0], v[1], v[2], v[3]);
-      sm.cxy1[slot] = make_float2(v[4], v[5]);
-      sm.cz[slot] = make_float4(__ldg(zp), __ldg(zp + 1), __ldg(zp + 2), 0.f);
-      sm.cmask[slot] = m;
-      sm.cface[slot] = e.x;
+    // cull against the tile, gather the face record (candidate id = position in the round)
+    uint32_t m = 0;
+    if (tid < cnt) {
+      const int4 e = sm.stage[k & 1][tid];
+      m = tile_mask(e, c.tile_x0, c.tile_y0);
+      if (m) {
+        const int64_t g = c.fbase + e.x;
+        float v[6];
+        load_xy(s, g, v);
+        const float* zp = s.z + g * 3;
+        sm.cxy0[tid] = make_float4(v[0], v[1], v[2], v[3]);
+        sm.cxy1[tid] = make_float2(v[4], v[5]);
+        sm.cz[tid] = make_float4(__ldg(zp), __ldg(zp + 1), __ldg(zp + 2), 0.f);
+        sm.cface[tid] = e.x;
+      }
     }
+    if ((tid & ~31) < cnt) store_bit_matrix(m, sm.colbits, sm.rowbits, tid >> 5);
     __syncthreads();
-    const int n = sm.ncand;
-    for (int j = 0; j < n; ++j) {
-      if ((sm.cmask[j] & c.sel) != c.sel) continue;
-      const float4 q0 = sm.cxy0[j];
-      const float2 q1 = sm.cxy1[j];
-      float w0, w1, w2;
-      if (!raster_weights(rc, c.x0, c.y0, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, w0, w1, w2)) continue;
-      const float4 zz = sm.cz[j];
-      const float zv = raster_depth(zz.x, zz.y, zz.z, w0, w1, w2);
-      const int f = sm.cface[j];
-      // reference: strict '>' in ascending face order == (z, lowest index) maximum
-      if (!(zv <= o.z) || (zv == o.z && f < o.f)) { o.z = zv; o.f = f; o.w0 = w0; o.w1 = w1; o.w2 = w2; }
+    const int ngroups = (cnt + 31) >> 5;
+    for (int g = 0; g < ngroups; ++g) {
+      uint32_t bits = sm.colbits[g][c.lx] & sm.rowbits[g][c.ly];
+      while (bits) {  // lane-private walk over this pixel's rectangle hits
+        const int j = (g << 5) + __ffs(bits) - 1;
+        bits &= bits - 1;
+        const float4 q0 = sm.cxy0[j];
+        const float2 q1 = sm.cxy1[j];
+        float w0, w1, w2;
+        if (!raster_weights(rc, c.x0, c.y0, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, w0, w1, w2)) continue;
+        const float4 zz = sm.cz[j];
+        const float zv = raster_depth(zz.x, zz.y, zz.z, w0, w1, w2);
+        const int f = sm.cface[j];
+        // reference: strict '>' in ascending face order == (z, lowest index) maximum
+        if (!(zv <= o.z) || (zv == o.z && f < o.f)) { o.z = zv; o.f = f; o.w0 = w0; o.w1 = w1; o.w2 = w2; }
+      }
     }
     if (k + 1 < nrounds) __syncthreads();
   }
@@ -408,8 +447,8 @@ __device__ __forceinline__ void raster_tile(const Scene& s, const TileCtx& c, co
 // Soft mask of one tile (forward) / its gradient (backward).  Candidates are the
 // faces of the "large" bins whose enlarged rectangle meets the tile, visited in
 // ascending face index; a pixel stops after knum hits.
-template <bool FILTER_ONLY_COUNT>
-__device__ __forceinline__ int soft_collect(const Scene& s, const TileCtx& c, TileSmem& sm, int lo, int hi) {
+template <bool FILTER_ONLY_COUNT, typename SM>
+__device__ __forceinline__ int soft_collect(const Scene& s, const TileCtx& c, SM& sm, int lo, int hi) {
   const int tid = threadIdx.x, lane = tid & 31;
   if (tid == 0) sm.nsoft = 0;
   __syncthreads();
@@ -443,28 +482,66 @@ struct SoftFwdOut {
   float* prob; int64_t* idx; uint8_t* type;  // K-lists (nullable)
 };
 
-__device__ __forceinline__ size_t tile_linear(const Scene& s, const TileCtx& c) {
-  return ((size_t)c.b * s.nty[0] + c.ty) * s.ntx[0] + c.tx;
+__device__ __forceinline__ int tile_linear(const Scene& s, const TileCtx& c) {
+  return (c.b * s.nty[0] + c.ty) * s.ntx[0] + c.tx;
 }
 
+struct SoftIO {
+  float* out_soft;                                   // forward
+  SoftFwdOut kl;                                     // forward, operator contract (nullable)
+  const float* grad_soft; const float* soft;         // backward
+  float* grad_xy;                                    // backward
+};
+
+// Soft mask of one tile.  `uncovered` is the calling thread's own pixel; the
+// uncovered pixels of the tile are first compacted so that the expensive
+// per-(pixel, face) distance work runs on densely packed warps (thread t owns the
+// t-th uncovered pixel).  Covered pixels (soft = 1) are written by their own thread.
 // CACHE (forward only): every hit (pixel, face, prob, dist_type) is appended to the
 // tile's block of the hit cache so that the backward pass is a dense stream over
 // hits instead of a second walk (the reference stores 13*knum bytes per pixel).
 template <bool BWD, bool KLISTS>
-__device__ __forceinline__ void soft_tile(const Scene& s, const TileCtx& c, TileSmem& sm, bool active,
-                                          float sigmainv, int K, bool cache, float& allprob, int& kid,
-                                          const SoftFwdOut& kl, float dLdp, float soft_saved,
-                                          float* grad_xy) {
-  const int tid = threadIdx.x, lane = tid & 31;
-  allprob = 1.0f;
-  kid = 0;
-  if (!__syncthreads_or(active)) {
-    if (!BWD && cache && tid == 0) s.tile_mode[tile_linear(s, c)] = 0;
-    return;
+__device__ __forceinline__ void soft_tile(const Scene& s, const TileCtx& c, TileSmem& sm, bool uncovered,
+                                          float sigmainv, int K, bool cache, const SoftIO& io) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  if (!BWD && c.in_img && !uncovered) {
+    io.out_soft[c.pix] = 1.0f;
+    if (KLISTS) {  // padding the reference gets from at::zeros / at::full(-1)
+      for (int k = 0; k < K; ++k) {
+        const int64_t o = c.pix * K + k;
+        io.kl.prob[o] = 0.f; io.kl.idx[o] = -1; io.kl.type[o] = 0;
+      }
+    }
   }
+  const unsigned av = __ballot_sync(kFull, uncovered);
+  if (lane == 0) sm.wcount[warp] = __popc(av);
+  __syncthreads();
+  int before = 0, na = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const int cw = sm.wcount[w];
+    if (w < warp) before += cw;
+    na += cw;
+  }
+  if (na == 0) return;  // uniform
+  if (uncovered) sm.apix[before + __popc(av & ((1u << lane) - 1u))] = (uint8_t)(c.lx | (c.ly << 4));
   if (BWD) {
     for (int i = tid; i < kChunk * 6; i += kThreads) (&sm.acc[0][0])[i] = 0.f;
   }
+  __syncthreads();
+  // thread t now owns the t-th uncovered pixel
+  const bool active = tid < na;
+  int lx = 0, ly = 0;
+  if (active) { const int p = sm.apix[tid]; lx = p & 15; ly = p >> 4; }
+  const int px = c.tile_x0 + lx, py = c.tile_y0 + ly;
+  const float x0 = pix_x(s.grid, px), y0 = pix_y(s.grid, py);
+  const uint32_t sel = (1u << lx) | (1u << (16 + ly));
+  const int64_t pix = ((int64_t)c.b * s.H + py) * s.W + px;
+  float dLdp = 0.f, soft_saved = 0.f;
+  if (BWD && active) { dLdp = io.grad_soft[pix]; soft_saved = io.soft[pix]; }
+
+  float allprob = 1.0f;
+  int kid = 0;
   const int maxf = s.first ? (int)(__ldg(s.first + c.b + 1) - c.fbase) : s.F;
   const size_t E = (size_t)256 * s.pool_K;
   uint32_t* blk = nullptr;
@@ -489,11 +566,13 @@ __device__ __forceinline__ void soft_tile(const Scene& s, const TileCtx& c, Tile
         int slot = -1;
         if (n > 0) {
           slot = atomicAdd(s.pool_ctr, 1);
-          if (slot >= s.pool_tiles) slot = -1;
+          if (slot >= s.pool_tiles) {   // cache full: this tile is recomputed in backward
+            slot = -1;
+            s.fb_list[atomicAdd(s.fb_ctr, 1)] = tile_linear(s, c);
+          }
         }
         sm.pool_slot = slot;
         sm.nent = 0;
-        s.tile_mode[tile_linear(s, c)] = n == 0 ? 0 : (slot >= 0 ? 1 : 2);
       }
       __syncthreads();
       if (sm.pool_slot >= 0) blk = s.pool_data + (size_t)sm.pool_slot * 3 * E;
@@ -520,50 +599,52 @@ __device__ __forceinline__ void soft_tile(const Scene& s, const TileCtx& c, Tile
         sm.cface[tid] = f;
       }
       __syncthreads();
-      for (int j = 0; j < cn; ++j) {
-        const bool hit = active && kid < K && ((sm.cmask[j] & c.sel) == c.sel);
-        float g[6];
-        float prob = 0.f;
-        int edgeid = 0;
-        if (hit) {
-          const float4 q0 = sm.cxy0[j];
-          const float2 q1 = sm.cxy1[j];
-          const float v[6] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y};
-          const float d2 = soft_min_dist(c.x0, c.y0, v, s.multiplier, edgeid);
-          prob = soft_prob(d2, sigmainv, s.multiplier);
-          if (!BWD) {
-            allprob = soft_accumulate(allprob, prob);
-            if (KLISTS) {
-              const int64_t o = c.pix * K + kid;
-              kl.prob[o] = prob; kl.idx[o] = sm.cface[j]; kl.type[o] = (uint8_t)(edgeid + 1);
+      if (warp * 32 < na) {  // warps that own no uncovered pixel have nothing to do
+        for (int j = 0; j < cn; ++j) {
+          const bool hit = active && kid < K && ((sm.cmask[j] & sel) == sel);
+          float g[6];
+          float prob = 0.f;
+          int edgeid = 0;
+          if (hit) {
+            const float4 q0 = sm.cxy0[j];
+            const float2 q1 = sm.cxy1[j];
+            const float v[6] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y};
+            const float d2 = soft_min_dist(x0, y0, v, s.multiplier, edgeid);
+            prob = soft_prob(d2, sigmainv, s.multiplier);
+            if (!BWD) {
+              allprob = soft_accumulate(allprob, prob);
+              if (KLISTS) {
+                const int64_t o = pix * K + kid;
+                io.kl.prob[o] = prob; io.kl.idx[o] = sm.cface[j]; io.kl.type[o] = (uint8_t)(edgeid + 1);
+              }
+            } else {
+              soft_backward_terms(x0, y0, v, edgeid, prob, soft_saved, dLdp, sigmainv, s.multiplier, g);
             }
-          } else {
-            soft_backward_terms(c.x0, c.y0, v, edgeid, prob, soft_saved, dLdp, sigmainv, s.multiplier, g);
+            ++kid;
           }
-          ++kid;
-        }
-        if (!BWD && blk != nullptr) {
-          const unsigned vote = __ballot_sync(kFull, hit);
-          if (vote) {
-            int wb = 0;
-            if (lane == 0) wb = atomicAdd(&sm.nent, __popc(vote));
-            wb = __shfl_sync(kFull, wb, 0);
-            if (hit) {
-              const size_t e = (size_t)wb + __popc(vote & ((1u << lane) - 1u));
-              blk[e] = (uint32_t)sm.cface[j];
-              blk[E + e] = __float_as_uint(prob);
-              blk[2 * E + e] = (uint32_t)c.lx | ((uint32_t)c.ly << 4) | ((uint32_t)(edgeid + 1) << 8);
+          if (!BWD && blk != nullptr) {
+            const unsigned vote = __ballot_sync(kFull, hit);
+            if (vote) {
+              int wb = 0;
+              if (lane == 0) wb = atomicAdd(&sm.nent, __popc(vote));
+              wb = __shfl_sync(kFull, wb, 0);
+              if (hit) {
+                const size_t e = (size_t)wb + __popc(vote & ((1u << lane) - 1u));
+                blk[e] = (uint32_t)sm.cface[j];
+                blk[E + e] = __float_as_uint(prob);
+                blk[2 * E + e] = (uint32_t)lx | ((uint32_t)ly << 4) | ((uint32_t)(edgeid + 1) << 8);
+              }
             }
           }
-        }
-        if (BWD) {
-          if (__any_sync(kFull, hit)) {
+          if (BWD) {
+            if (__any_sync(kFull, hit)) {
 #pragma unroll
-            for (int q = 0; q < 6; ++q) {
-              float x = hit ? g[q] : 0.f;
+              for (int q = 0; q < 6; ++q) {
+                float x = hit ? g[q] : 0.f;
 #pragma unroll
-              for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(kFull, x, d);
-              if (lane == 0 && x != 0.f) atomicAdd(&sm.acc[j][q], x);
+                for (int d = 16; d > 0; d >>= 1) x += __shfl_xor_sync(kFull, x, d);
+                if (lane == 0 && x != 0.f) atomicAdd(&sm.acc[j][q], x);
+              }
             }
           }
         }
@@ -571,7 +652,7 @@ __device__ __forceinline__ void soft_tile(const Scene& s, const TileCtx& c, Tile
       all_done = __syncthreads_and(!active || kid >= K);
       if (BWD) {
         if (tid < cn) {
-          float* gp = grad_xy + (c.fbase + sm.cface[tid]) * 6;
+          float* gp = io.grad_xy + (c.fbase + sm.cface[tid]) * 6;
 #pragma unroll
           for (int q = 0; q < 6; ++q) {
             const float x = sm.acc[tid][q];
@@ -584,8 +665,238 @@ __device__ __forceinline__ void soft_tile(const Scene& s, const TileCtx& c, Tile
     if (hi == 0x7fffffff || all_done) break;
     lo = hi;
   }
-  if (!BWD && blk != nullptr && tid == 0)
-    s.pool_hdr[sm.pool_slot] = make_int4(c.b, c.tx, c.ty, sm.nent);
+  if (!BWD) {
+    if (active) {
+      io.out_soft[pix] = soft_finish(allprob);
+      if (KLISTS) {
+        for (int k = kid; k < K; ++k) {
+          const int64_t o = pix * K + k;
+          io.kl.prob[o] = 0.f; io.kl.idx[o] = -1; io.kl.type[o] = 0;
+        }
+      }
+    }
+    if (blk != nullptr && tid == 0) s.pool_hdr[sm.pool_slot] = make_int4(c.b, c.tx, c.ty, sm.nent);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Soft mask forward of one tile, pair-parallel.  The uncovered pixels are
+// compacted; in rounds, every pixel claims its next (<= kRound) faces in ascending
+// index (respecting knum) straight from its hit bit words, the claimed (pixel, face)
+// pairs are laid out face-major in shared memory, ALL 256 threads evaluate the
+// expensive distance/probability of one pair each, and finally every pixel folds
+// its own results in order — the same sequence of fp32/fp64 operations per pixel as
+// the reference's sequential loop, with the work spread over every lane.
+struct SoftSmem {
+  unsigned long long list[kSoftCap];     // (face << 32) | mask, unsorted
+  unsigned long long sorted[kSoftCap];
+  float4 cxy0[kChunk];
+  float2 cxy1[kChunk];
+  int cface[kChunk];
+  uint32_t colbits[kChunk / 32][16];
+  uint32_t rowbits[kChunk / 32][16];
+  int cnt_c[kChunk];                     // claims per face in this round
+  int off_c[kChunk];                     // face-major pair offsets
+  float res_prob[kPairCap];
+  uint16_t claim[kThreads][kRound];      // per pixel: (face | pos << 8), then the pair slot
+  uint8_t pair_cand[kPairCap];
+  uint8_t pair_pix[kPairCap];
+  uint8_t res_type[kPairCap];
+  uint8_t apix[kThreads];
+  BinRef bin[2][kMaxLevels];
+  int wcount[kThreads / 32];
+  int nsoft, nent, pool_slot, npairs;
+};
+
+template <bool KLISTS>
+__device__ __forceinline__ void soft_tile_fwd(const Scene& s, const TileCtx& c, SoftSmem& sm, bool uncovered,
+                                              float sigmainv, int K, bool cache, const SoftIO& io) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned av = __ballot_sync(kFull, uncovered);
+  if (lane == 0) sm.wcount[warp] = __popc(av);
+  __syncthreads();
+  int before = 0, na = 0;
+#pragma unroll
+  for (int w = 0; w < kThreads / 32; ++w) {
+    const int cw = sm.wcount[w];
+    if (w < warp) before += cw;
+    na += cw;
+  }
+  if (na == 0) return;  // uniform
+  if (uncovered) sm.apix[before + __popc(av & ((1u << lane) - 1u))] = (uint8_t)(c.lx | (c.ly << 4));
+  __syncthreads();
+  const bool active = tid < na;  // thread t owns the t-th uncovered pixel
+  int lx = 0, ly = 0;
+  if (active) { const int p = sm.apix[tid]; lx = p & 15; ly = p >> 4; }
+  const int64_t pix = ((int64_t)c.b * s.H + (c.tile_y0 + ly)) * s.W + (c.tile_x0 + lx);
+
+  float allprob = 1.0f;
+  int kid = 0;
+  const int maxf = s.first ? (int)(__ldg(s.first + c.b + 1) - c.fbase) : s.F;
+  const size_t E = (size_t)256 * s.pool_K;
+  uint32_t* blk = nullptr;
+  bool first_window = true;
+  int lo = -1;
+  while (true) {
+    int hi = 0x7fffffff;
+    int n = soft_collect<false>(s, c, sm, lo, hi);
+    if (n > kSoftCap) {
+      // pathological density: take the largest window (lo, hi] holding <= kSoftCap candidates
+      int L = lo + 1, R = maxf - 1;
+      while (L < R) {
+        const int mid = L + (R - L + 1) / 2;
+        if (soft_collect<true>(s, c, sm, lo, mid) <= kSoftCap) L = mid; else R = mid - 1;
+      }
+      hi = L;
+      n = soft_collect<false>(s, c, sm, lo, hi);
+    }
+    if (first_window) {
+      first_window = false;
+      if (tid == 0) {
+        int slot = -1;
+        if (cache && n > 0) {
+          slot = atomicAdd(s.pool_ctr, 1);
+          if (slot >= s.pool_tiles) {   // cache full: this tile is recomputed in backward
+            slot = -1;
+            s.fb_list[atomicAdd(s.fb_ctr, 1)] = tile_linear(s, c);
+          }
+        }
+        sm.pool_slot = slot;
+        sm.nent = 0;
+      }
+      __syncthreads();
+      if (sm.pool_slot >= 0) blk = s.pool_data + (size_t)sm.pool_slot * 3 * E;
+    }
+    // rank sort by face index (keys are unique: a face lives in one level, a tile reads one bin per level)
+    for (int j = tid; j < n; j += kThreads) {
+      const unsigned long long key = sm.list[j];
+      int rank = 0;
+      for (int i = 0; i < n; ++i) rank += (sm.list[i] < key) ? 1 : 0;
+      sm.sorted[rank] = key;
+    }
+    __syncthreads();
+    bool all_done = false;
+    for (int c0 = 0; c0 < n && !all_done; c0 += kChunk) {
+      const int cn = min(kChunk, n - c0);
+      const int ngroups = (cn + 31) >> 5;
+      uint32_t m = 0;
+      if (tid < cn) {
+        const unsigned long long key = sm.sorted[c0 + tid];
+        const int f = (int)(key >> 32);
+        m = (uint32_t)key;
+        float v[6];
+        load_xy(s, c.fbase + f, v);
+        sm.cxy0[tid] = make_float4(v[0], v[1], v[2], v[3]);
+        sm.cxy1[tid] = make_float2(v[4], v[5]);
+        sm.cface[tid] = f;
+      }
+      if (warp < ngroups) store_bit_matrix(m, sm.colbits, sm.rowbits, warp);
+      sm.cnt_c[tid] = 0;
+      __syncthreads();
+      int g = 0;              // hit word being consumed by this pixel
+      uint32_t bits = active ? (sm.colbits[0][lx] & sm.rowbits[0][ly]) : 0u;
+      while (true) {
+        // claim the next <= kRound faces of this pixel, in index order
+        int took = 0;
+        if (active) {
+          while (took < kRound && kid + took < K) {
+            while (bits == 0 && g + 1 < ngroups) { ++g; bits = sm.colbits[g][lx] & sm.rowbits[g][ly]; }
+            if (bits == 0) break;
+            const int j = (g << 5) + __ffs(bits) - 1;
+            bits &= bits - 1;
+            const int pos = atomicAdd(&sm.cnt_c[j], 1);
+            sm.claim[tid][took] = (uint16_t)(j | (pos << 8));
+            ++took;
+          }
+        }
+        if (!__syncthreads_or(took > 0)) break;
+        // face-major offsets
+        if (warp == 0) {
+          int v[8], sum = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const int j = lane * 8 + i; v[i] = j < cn ? sm.cnt_c[j] : 0; sum += v[i]; }
+          int x = sum;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(kFull, x, d); if (lane >= d) x += y; }
+          int run = x - sum;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const int j = lane * 8 + i; if (j < cn) sm.off_c[j] = run; run += v[i]; }
+          if (lane == 31) sm.npairs = x;
+        }
+        __syncthreads();
+        const int T = sm.npairs;
+        const int ebase = sm.nent;
+        for (int i = 0; i < took; ++i) {
+          const int cl = sm.claim[tid][i];
+          const int j = cl & 0xff;
+          const int slot = sm.off_c[j] + (cl >> 8);
+          sm.pair_cand[slot] = (uint8_t)j;
+          sm.pair_pix[slot] = (uint8_t)tid;
+          sm.claim[tid][i] = (uint16_t)slot;
+        }
+        __syncthreads();
+        sm.cnt_c[tid] = 0;  // for the next round (ordered by the barrier below)
+        // dense evaluation: one (pixel, face) pair per thread
+        for (int u = tid; u < T; u += kThreads) {
+          const int j = sm.pair_cand[u];
+          const int p = sm.apix[sm.pair_pix[u]];
+          const int plx = p & 15, ply = p >> 4;
+          const float4 q0 = sm.cxy0[j];
+          const float2 q1 = sm.cxy1[j];
+          const float v[6] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y};
+          int edgeid;
+          const float d2 = soft_min_dist(pix_x(s.grid, c.tile_x0 + plx), pix_y(s.grid, c.tile_y0 + ply), v,
+                                         s.multiplier, edgeid);
+          const float prob = soft_prob(d2, sigmainv, s.multiplier);
+          sm.res_prob[u] = prob;
+          sm.res_type[u] = (uint8_t)(edgeid + 1);
+          if (blk != nullptr) {
+            const size_t e = (size_t)ebase + u;
+            blk[e] = (uint32_t)sm.cface[j];
+            blk[E + e] = __float_as_uint(prob);
+            blk[2 * E + e] = (uint32_t)plx | ((uint32_t)ply << 4) | ((uint32_t)(edgeid + 1) << 8);
+          }
+        }
+        __syncthreads();
+        if (tid == 0) sm.nent = ebase + T;
+        // every pixel folds its own results in face order
+        for (int i = 0; i < took; ++i) {
+          const int slot = sm.claim[tid][i];
+          const float prob = sm.res_prob[slot];
+          allprob = soft_accumulate(allprob, prob);
+          if (KLISTS) {
+            const int64_t o = pix * K + kid;
+            io.kl.prob[o] = prob; io.kl.idx[o] = sm.cface[sm.pair_cand[slot]]; io.kl.type[o] = sm.res_type[slot];
+          }
+          ++kid;
+        }
+      }
+      all_done = __syncthreads_and(!active || kid >= K);
+    }
+    if (hi == 0x7fffffff || all_done) break;
+    lo = hi;
+  }
+  if (active) io.out_soft[pix] = soft_finish(allprob);
+  if (blk != nullptr && tid == 0) s.pool_hdr[sm.pool_slot] = make_int4(c.b, c.tx, c.ty, sm.nent);
+}
+
+__device__ __forceinline__ TileCtx tile_ctx_from_linear(const Scene& s, int t) {
+  TileCtx c;
+  const int tiles_xy = s.ntx[0] * s.nty[0];
+  c.b = t / tiles_xy;
+  const int r = t - c.b * tiles_xy;
+  c.ty = r / s.ntx[0];
+  c.tx = r - c.ty * s.ntx[0];
+  c.tile_x0 = c.tx * kTile; c.tile_y0 = c.ty * kTile;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  c.lx = ((warp & 1) << 3) | (lane & 7);
+  c.ly = ((warp >> 1) << 2) | (lane >> 3);
+  c.px = c.tile_x0 + c.lx; c.py = c.tile_y0 + c.ly;
+  c.in_img = c.px < s.W && c.py < s.H;
+  c.x0 = 0.f; c.y0 = 0.f; c.sel = 0;
+  c.fbase = view_fbase(s, c.b);
+  c.pix = ((int64_t)c.b * s.H + c.py) * s.W + c.px;
+  return c;
 }
 
 // ---------------------------------------------------------------------------
@@ -603,7 +914,7 @@ struct FwdArgs {
 
 template <bool RASTER, bool SOFT, bool KLISTS>
 __global__ void __launch_bounds__(kThreads) dibr_tile_fwd_kernel(const __grid_constant__ FwdArgs a) {
-  __shared__ __align__(128) TileSmem sm;
+  __shared__ __align__(128) RasterSmem sm;
   const Scene& s = a.s;
   const int tid = threadIdx.x;
   const TileCtx c = make_tile_ctx(s);
@@ -632,29 +943,53 @@ __global__ void __launch_bounds__(kThreads) dibr_tile_fwd_kernel(const __grid_co
     best_f = c.in_img ? (int)a.idx[c.pix] : 0;
   }
   if (SOFT) {
-    const bool active = c.in_img && best_f < 0;
-    float allprob; int kid;
-    soft_tile<false, KLISTS>(s, c, sm, active, a.sigmainv, a.K, !KLISTS && a.cache != 0, allprob, kid,
-                             a.kl, 0.f, 0.f, nullptr);
+    // defaults (covered: 1; uncovered with no neighbour: 1 - 1 = 0) and K-list padding; tiles
+    // where an uncovered pixel may lie under an enlarged face go to the soft-mask work list
+    const bool uncovered = c.in_img && best_f < 0;
     if (c.in_img) {
-      a.out_soft[c.pix] = active ? soft_finish(allprob) : 1.0f;
+      a.out_soft[c.pix] = uncovered ? 0.0f : 1.0f;
       if (KLISTS) {  // padding the reference gets from at::zeros / at::full(-1)
-        for (int k = active ? kid : 0; k < a.K; ++k) {
+        for (int k = 0; k < a.K; ++k) {
           const int64_t o = c.pix * a.K + k;
           a.kl.prob[o] = 0.f; a.kl.idx[o] = -1; a.kl.type[o] = 0;
         }
       }
     }
+    const int any = __syncthreads_or(uncovered);
+    if (any && tid == 0) {
+      int nlarge = 0;
+      for (int l = 0; l < kMaxLevels; ++l) nlarge += sm.bin[1][l].n;
+      if (nlarge > 0) s.band_list[atomicAdd(s.band_ctr, 1)] = tile_linear(s, c);
+    }
+  }
+}
+
+// Soft-mask forward over the work list (persistent CTAs).
+template <bool KLISTS>
+__global__ void __launch_bounds__(kThreads, 3) soft_tiles_fwd_kernel(const __grid_constant__ FwdArgs a) {
+  extern __shared__ __align__(128) unsigned char soft_smem_raw[];
+  SoftSmem& sm = *reinterpret_cast<SoftSmem*>(soft_smem_raw);
+  const Scene& s = a.s;
+  const int total = min(*s.band_ctr, s.ntx[0] * s.nty[0] * s.B);
+  SoftIO io;
+  io.out_soft = a.out_soft; io.kl = a.kl; io.grad_soft = nullptr; io.soft = nullptr; io.grad_xy = nullptr;
+  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    const TileCtx c = tile_ctx_from_linear(s, s.band_list[w]);
+    __syncthreads();  // previous tile's shared state fully consumed
+    load_bin_table(s, c, sm);
+    __syncthreads();
+    soft_tile_fwd<KLISTS>(s, c, sm, c.in_img && a.idx[c.pix] < 0, a.sigmainv, a.K, !KLISTS && a.cache != 0, io);
   }
 }
 
 // ---------------------------------------------------------------------------
 // Soft-mask backward.  (1) dense kernel over the hit cache; (2) the recompute tile
-// kernel for tiles the cache could not hold (tile_mode == 2) or when no cache exists.
+// kernel for the tiles the cache could not hold (fb_list) or, with no forward state,
+// for every tile.  Persistent CTAs walk the work list.
 struct SoftBwdArgs {
   Scene s;
   float sigmainv; int K;
-  int only_mode2;            // 1: skip tiles whose hits are cached (or that have none)
+  int from_list;             // 1: tiles of fb_list only; 0: every tile
   const float* grad_soft; const float* soft; const int64_t* idx;
   float* grad_xy;
 };
@@ -662,21 +997,18 @@ struct SoftBwdArgs {
 __global__ void __launch_bounds__(kThreads) dibr_tile_soft_bwd_kernel(const __grid_constant__ SoftBwdArgs a) {
   __shared__ __align__(128) TileSmem sm;
   const Scene& s = a.s;
-  const TileCtx c = make_tile_ctx(s);
-  if (a.only_mode2 && s.tile_mode[tile_linear(s, c)] != 2) return;
-  load_bin_table(s, c, sm);
-  __syncthreads();
-  bool active = false;
-  float dLdp = 0.f, soft_saved = 0.f;
-  if (c.in_img && a.idx[c.pix] < 0) {
-    active = true;
-    dLdp = a.grad_soft[c.pix];
-    soft_saved = a.soft[c.pix];
+  const int ntiles = s.ntx[0] * s.nty[0] * s.B;
+  const int total = a.from_list ? min(*s.fb_ctr, ntiles) : ntiles;
+  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    const TileCtx c = tile_ctx_from_linear(s, a.from_list ? s.fb_list[w] : w);
+    __syncthreads();  // previous tile's shared state fully consumed
+    load_bin_table(s, c, sm);
+    __syncthreads();
+    SoftIO io;
+    io.out_soft = nullptr; io.kl = SoftFwdOut{nullptr, nullptr, nullptr};
+    io.grad_soft = a.grad_soft; io.soft = a.soft; io.grad_xy = a.grad_xy;
+    soft_tile<true, false>(s, c, sm, c.in_img && a.idx[c.pix] < 0, a.sigmainv, a.K, false, io);
   }
-  float allprob; int kid;
-  SoftFwdOut none = {nullptr, nullptr, nullptr};
-  soft_tile<true, false>(s, c, sm, active, a.sigmainv, a.K, false, allprob, kid, none, dLdp, soft_saved,
-                         a.grad_xy);
 }
 
 template <int N>
@@ -894,16 +1226,16 @@ int bins_per_view(int H, int W) {
 }
 
 // Workspace layout (all pieces 256-byte aligned):
-//   cnt [2*B*NB] int + pool_ctr | off [2*B*NB] int | tile_mode [tiles] u8 |
+//   cnt [2*B*NB] int + pool_ctr + fb_ctr + band_ctr | off [2*B*NB] int | fb_list, band_list [tiles] int |
 //   entries [2*4*NF] int4 | pool_hdr [pool_tiles] int4 | pool_data [pool_tiles][3][256*K] u32
 struct Layout { size_t cnt, off, mode, ent, base; };
 
 Layout layout_for(int B, int64_t NF, int H, int W) {
   Layout L;
   const size_t tiles = (size_t)((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile) * B;
-  L.cnt = align_up(((size_t)2 * B * bins_per_view(H, W) + 1) * sizeof(int), 256);
+  L.cnt = align_up(((size_t)2 * B * bins_per_view(H, W) + 3) * sizeof(int), 256);
   L.off = align_up((size_t)2 * B * bins_per_view(H, W) * sizeof(int), 256);
-  L.mode = align_up(tiles, 256);
+  L.mode = 2 * align_up(tiles * sizeof(int), 256);
   L.ent = align_up((size_t)2 * 4 * (size_t)(NF > 0 ? NF : 1) * sizeof(int4), 256);
   L.base = L.cnt + L.off + L.mode + L.ent + 256;
   return L;
@@ -942,9 +1274,11 @@ int setup_scene(Scene& s, int B, int64_t NF, int F, int H, int W, float multipli
   s.NB = nb;
   s.cnt = (int*)p;
   s.pool_ctr = s.cnt + (size_t)2 * B * nb;
+  s.fb_ctr = s.pool_ctr + 1;
+  s.band_ctr = s.pool_ctr + 2;
   p += Lo.cnt;
   s.off = (int*)p; p += Lo.off;
-  s.tile_mode = (uint8_t*)p; p += Lo.mode;
+  s.fb_list = (int*)p; s.band_list = (int*)(p + Lo.mode / 2); p += Lo.mode;
   s.entries = (int4*)p; p += Lo.ent;
   s.pool_tiles = 0; s.pool_K = knum > 0 ? knum : 1; s.pool_hdr = nullptr; s.pool_data = nullptr;
   if (knum > 0) {
@@ -964,7 +1298,7 @@ int setup_scene(Scene& s, int B, int64_t NF, int F, int H, int W, float multipli
 }
 
 int build_bins(const Scene& s, int sets, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(s.cnt, 0, ((size_t)2 * s.B * s.NB + 1) * sizeof(int), st);
+  cudaError_t e = cudaMemsetAsync(s.cnt, 0, ((size_t)2 * s.B * s.NB + 3) * sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
   if (s.NF > 0) {
     const unsigned blocks = (unsigned)((s.NF + 255) / 256);
@@ -977,9 +1311,30 @@ int build_bins(const Scene& s, int sets, cudaStream_t st) {
 
 dim3 tile_grid(const Scene& s) { return dim3((unsigned)s.ntx[0], (unsigned)s.nty[0], (unsigned)s.B); }
 
+// Persistent kernels: one resident wave (SMs x CTAs that fit per SM), never more than the tiles.
+template <typename Kernel>
+unsigned persistent_grid(const Scene& s, Kernel kernel, size_t dyn_smem = 0) {
+  int dev = 0, sms = 148, per_sm = 2;
+  if (cudaGetDevice(&dev) == cudaSuccess) {
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, dyn_smem) != cudaSuccess ||
+        per_sm < 1)
+      per_sm = 2;
+  }
+  const int64_t ntiles = (int64_t)s.ntx[0] * s.nty[0] * s.B;
+  const int64_t g = (int64_t)sms * per_sm;
+  return (unsigned)(ntiles < g ? ntiles : g);
+}
+
 template <bool R, bool S, bool K>
 void launch_fwd(const FwdArgs& a, cudaStream_t st) {
   dibr_tile_fwd_kernel<R, S, K><<<tile_grid(a.s), kThreads, 0, st>>>(a);
+  if (S) {
+    cudaFuncSetAttribute(soft_tiles_fwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)sizeof(SoftSmem));
+    soft_tiles_fwd_kernel<K><<<persistent_grid(a.s, soft_tiles_fwd_kernel<K>, sizeof(SoftSmem)), kThreads,
+                               sizeof(SoftSmem), st>>>(a);
+  }
 }
 
 int launch_raster_bwd(const RasterBwdArgs& a, cudaStream_t st) {
@@ -1044,7 +1399,7 @@ int dibr_b200_forward(int batch, int num_faces, int height, int width, int feat_
   if (rc) return rc;
   a.rc = make_raster_const(eps);
   a.D = feat_dim; a.feat = face_features; a.sigmainv = sigmainv; a.K = knum;
-  a.cache = soft ? 1 : 0;   // tile_mode is always written; hits are cached while blocks last
+  a.cache = soft ? 1 : 0;   // hits are cached while blocks last; other tiles go to fb_list
   a.out_feat = interpolated_features; a.idx = face_idx; a.out_w = output_weights; a.out_soft = soft_mask;
   a.kl = SoftFwdOut{nullptr, nullptr, nullptr};
   if (raster && soft) launch_fwd<true, true, false>(a, st);
@@ -1095,17 +1450,18 @@ int dibr_b200_backward(int batch, int num_faces, int height, int width, int feat
     s.fnz = nullptr; s.valid = nullptr; s.bbox_tight = nullptr; s.bbox_large = nullptr;
     a.sigmainv = sigmainv; a.K = knum; a.grad_soft = grad_soft_mask; a.soft = soft_mask;
     a.idx = face_idx; a.grad_xy = grad_face_vertices_image;
+    const unsigned persistent = persistent_grid(s, dibr_tile_soft_bwd_kernel);
     if (!bins_valid) {
       // no forward state: rebuild the large bins and recompute every tile
       rc = build_bins(s, 2, st);
       if (rc) return rc;
-      a.only_mode2 = 0;
-      dibr_tile_soft_bwd_kernel<<<tile_grid(s), kThreads, 0, st>>>(a);
+      a.from_list = 0;
+      dibr_tile_soft_bwd_kernel<<<persistent, kThreads, 0, st>>>(a);
     } else {
-      // forward left bins + tile_mode + the hit cache in the workspace
-      a.only_mode2 = 1;
+      // forward left the bins, the hit cache and the list of tiles it could not cache
+      a.from_list = 1;
       if (s.pool_tiles > 0) soft_bwd_dense_kernel<<<(unsigned)s.pool_tiles, kThreads, 0, st>>>(a);
-      dibr_tile_soft_bwd_kernel<<<tile_grid(s), kThreads, 0, st>>>(a);
+      dibr_tile_soft_bwd_kernel<<<persistent, kThreads, 0, st>>>(a);
     }
     return (int)cudaGetLastError();
   }
