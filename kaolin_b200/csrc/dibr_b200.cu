@@ -33,7 +33,7 @@ constexpr int kThreads = 256;
 constexpr int kChunk = 256;
 constexpr int kMaxLevels = 6;   // 16 * 4^5 = 16384 px
 constexpr int kSoftCap = 1024;  // soft-mask candidates sorted per pass
-constexpr int kRound = 16;      // hits a pixel contributes to one pair round
+constexpr int kRound = 12;      // hits a pixel contributes to one pair round
 constexpr int kPairCap = kThreads * kRound;
 constexpr unsigned kFull = 0xffffffffu;
 
@@ -966,7 +966,7 @@ __global__ void __launch_bounds__(kThreads) dibr_tile_fwd_kernel(const __grid_co
 
 // Soft-mask forward over the work list (persistent CTAs).
 template <bool KLISTS>
-__global__ void __launch_bounds__(kThreads, 3) soft_tiles_fwd_kernel(const __grid_constant__ FwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 4) soft_tiles_fwd_kernel(const __grid_constant__ FwdArgs a) {
   extern __shared__ __align__(128) unsigned char soft_smem_raw[];
   SoftSmem& sm = *reinterpret_cast<SoftSmem*>(soft_smem_raw);
   const Scene& s = a.s;
