@@ -84,7 +84,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                 "-lms", "100", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
+                 "-lms", "20", "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL,
                 text=True)
         except Exception:
             self.proc = None
