@@ -1023,17 +1023,23 @@ __global__ void __launch_bounds__(kThreads) soft_bwd_dense_kernel(const __grid_c
   const uint32_t* blk = s.pool_data + (size_t)blockIdx.x * 3 * E;
   const int64_t fbase = view_fbase(s, h.x);
   const int tid = threadIdx.x, lane = tid & 31;
+  uint32_t nface = 0, nprob = 0, nmeta = 0;
+  if (tid < h.w) { nface = __ldcs(blk + tid); nprob = __ldcs(blk + E + tid); nmeta = __ldcs(blk + 2 * E + tid); }
   for (int base = 0; base < h.w; base += kThreads) {
     const int t = base + tid;
     const bool valid = t < h.w;
+    const uint32_t cface = nface, cprob = nprob, meta = nmeta;
+    if (t + kThreads < h.w) {  // next batch of hits: requested before this one is processed
+      nface = __ldcs(blk + t + kThreads); nprob = __ldcs(blk + E + t + kThreads);
+      nmeta = __ldcs(blk + 2 * E + t + kThreads);
+    }
     int face = -1 - lane;
     float g[6];
 #pragma unroll
     for (int q = 0; q < 6; ++q) g[q] = 0.f;
     if (valid) {
-      face = (int)blk[t];
-      const float prob = __uint_as_float(blk[E + t]);
-      const uint32_t meta = blk[2 * E + t];
+      face = (int)cface;
+      const float prob = __uint_as_float(cprob);
       const int px = h.y * kTile + (int)(meta & 15u), py = h.z * kTile + (int)((meta >> 4) & 15u);
       const int64_t pix = ((int64_t)h.x * s.H + py) * s.W + px;
       float v[6];
@@ -1093,17 +1099,28 @@ __global__ void __launch_bounds__(kThreads) raster_bwd_kernel(const __grid_const
   const bool in_img = px < a.W && py < a.H;
   const int64_t pix = ((int64_t)b * a.H + py) * a.W + px;
   const int D = DT > 0 ? DT : a.D;
+  // all streaming operands of the pixel are requested together (weights and upstream
+  // gradient do not depend on face_idx): one exposed HBM latency instead of two
   int f = -1;
-  if (in_img) f = (int)a.idx[pix];
+  float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+  float gpre[DT > 0 ? DT : 1];
+#pragma unroll
+  for (int d = 0; d < (DT > 0 ? DT : 1); ++d) gpre[d] = 0.f;
+  if (in_img) {
+    const float* wp = a.w + pix * 3;
+    f = (int)__ldcs(a.idx + pix);
+    w0 = __ldcs(wp); w1 = __ldcs(wp + 1); w2 = __ldcs(wp + 2);
+    if (DT > 0) {
+#pragma unroll
+      for (int d = 0; d < DT; ++d) gpre[d] = __ldcs(a.grad_feat + pix * DT + d);
+    }
+  }
   if (!__any_sync(kFull, f >= 0)) return;
   const bool cov = f >= 0;
   const int64_t face = (int64_t)b * a.F + (cov ? f : 0);
 
-  float w0 = 0.f, w1 = 0.f, w2 = 0.f;
   RasterBwdGeom G;
   if (cov) {
-    const float* wp = a.w + pix * 3;
-    w0 = wp[0]; w1 = wp[1]; w2 = wp[2];
     const float2* pp = reinterpret_cast<const float2*>(a.xy + face * 6);
     const float2 pa = __ldg(pp), pb = __ldg(pp + 1), pc = __ldg(pp + 2);
     const float p[6] = {pa.x, pa.y, pb.x, pb.y, pc.x, pc.y};
@@ -1123,7 +1140,7 @@ __global__ void __launch_bounds__(kThreads) raster_bwd_kernel(const __grid_const
     for (int d = 0; d < DT; ++d) {
       float g = 0.f;
       if (cov) {
-        g = gp[d];
+        g = gpre[d];
         float t6[6];
         raster_backward_feature(G, g, __ldg(cf + d), __ldg(cf + DT + d), __ldg(cf + 2 * DT + d), t6);
 #pragma unroll

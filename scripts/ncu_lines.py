@@ -89,7 +89,7 @@ def main():
     print(kname)
     print(f"total warp instr {tot_i:,}  samples {tot_s:,}")
     # ---- by enclosing function of the main .cu (phase view) ----
-    cu = os.path.join(os.path.dirname(os.path.abspath(lib)), "dibr_b200.cu")
+    cu = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "kaolin_b200", "csrc", "dibr_b200.cu")
     fn_at = {}
     if os.path.exists(cu):
         cur_fn = "?"
