@@ -332,6 +332,7 @@ struct RasterSmem {
   uint32_t rowbits[kChunk / 32][16];     // [group][tile row]
   unsigned long long bar[2];
   BinRef bin[2][kMaxLevels];
+  int any_uncovered, warps_done;
 };
 
 // Transposes the tile-local rectangle masks of the 32 candidates held by a warp
@@ -913,12 +914,13 @@ struct FwdArgs {
 };
 
 template <bool RASTER, bool SOFT, bool KLISTS>
-__global__ void __launch_bounds__(kThreads) dibr_tile_fwd_kernel(const __grid_constant__ FwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 6) dibr_tile_fwd_kernel(const __grid_constant__ FwdArgs a) {
   __shared__ __align__(128) RasterSmem sm;
   const Scene& s = a.s;
   const int tid = threadIdx.x;
   const TileCtx c = make_tile_ctx(s);
   if (RASTER && tid == 32) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_fence_init(); }
+  if (tid == 64) { sm.any_uncovered = 0; sm.warps_done = 0; }
   load_bin_table(s, c, sm);
   __syncthreads();
   int best_f;
@@ -931,7 +933,16 @@ __global__ void __launch_bounds__(kThreads) dibr_tile_fwd_kernel(const __grid_co
       float* wp = a.out_w + c.pix * 3;
       wp[0] = o.w0; wp[1] = o.w1; wp[2] = o.w2;
       float* fp = a.out_feat + c.pix * a.D;
-      if (o.f >= 0) {
+      if (a.D == 3) {  // the DIB-R tutorial shape (uv + mask), fully unrolled
+        float r[3] = {0.f, 0.f, 0.f};
+        if (o.f >= 0) {
+          const float* ff = a.feat + (c.fbase + o.f) * 9;
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+            r[d] = raster_interp(__ldg(ff + d), __ldg(ff + 3 + d), __ldg(ff + 6 + d), o.w0, o.w1, o.w2);
+        }
+        fp[0] = r[0]; fp[1] = r[1]; fp[2] = r[2];
+      } else if (o.f >= 0) {
         const float* ff = a.feat + (c.fbase + o.f) * 3 * a.D;
         for (int d = 0; d < a.D; ++d)
           fp[d] = raster_interp(__ldg(ff + d), __ldg(ff + a.D + d), __ldg(ff + 2 * a.D + d), o.w0, o.w1, o.w2);
@@ -955,11 +966,16 @@ __global__ void __launch_bounds__(kThreads) dibr_tile_fwd_kernel(const __grid_co
         }
       }
     }
-    const int any = __syncthreads_or(uncovered);
-    if (any && tid == 0) {
-      int nlarge = 0;
-      for (int l = 0; l < kMaxLevels; ++l) nlarge += sm.bin[1][l].n;
-      if (nlarge > 0) s.band_list[atomicAdd(s.band_ctr, 1)] = tile_linear(s, c);
+    // no CTA barrier: warps retire independently; the last one to finish files the tile
+    const unsigned wv = __ballot_sync(kFull, uncovered);
+    if ((tid & 31) == 0) {
+      if (wv) atomicOr(&sm.any_uncovered, 1);
+      __threadfence_block();
+      if (atomicAdd(&sm.warps_done, 1) == kThreads / 32 - 1 && atomicOr(&sm.any_uncovered, 0)) {
+        int nlarge = 0;
+        for (int l = 0; l < kMaxLevels; ++l) nlarge += sm.bin[1][l].n;
+        if (nlarge > 0) s.band_list[atomicAdd(s.band_ctr, 1)] = tile_linear(s, c);
+      }
     }
   }
 }
@@ -1091,7 +1107,7 @@ struct RasterBwdArgs {
 };
 
 template <int DT>  // DT > 0: feature dim known at compile time; 0: runtime loop
-__global__ void __launch_bounds__(kThreads) raster_bwd_kernel(const __grid_constant__ RasterBwdArgs a) {
+__global__ void __launch_bounds__(kThreads, 6) raster_bwd_kernel(const __grid_constant__ RasterBwdArgs a) {
   const int tx = blockIdx.x, ty = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int px = tx * kTile + (((warp & 1) << 3) | (lane & 7));
