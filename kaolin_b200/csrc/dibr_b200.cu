@@ -66,6 +66,9 @@ struct Scene {
   int* pool_ctr;          // [1] blocks handed out
   int4* pool_hdr;         // [pool_tiles] {b, tx, ty, hits}
   uint32_t* pool_data;    // [pool_tiles][3][256*K]: face | prob bits | lx|ly<<4|(dist_type)<<8
+  int* pool_na;           // [pool_tiles] uncovered pixels of the tile           } only when
+  uint32_t* pool_aux;     // [pool_tiles][256] per such pixel: lx|ly<<4 | hits<<8 } knum <= 32:
+  uint16_t* pool_slots;   // [pool_tiles][256][32] its hit slots, face order      } 3-kernel forward
   int* fb_ctr;            // [1] tiles whose hits did not fit the cache (recomputed in backward)
   int* fb_list;           // [B*nty*ntx] their linear tile ids
   int* band_ctr;          // [1] tiles with uncovered pixels under some enlarged face rectangle
@@ -909,6 +912,7 @@ struct FwdArgs {
   const float* feat;        // (NF,3,D)
   float sigmainv; int K;
   int cache;                // fill the soft-mask hit cache
+  int from_fb;              // soft_tiles_fwd_kernel: walk fb_list instead of band_list
   float* out_feat; int64_t* idx; float* out_w; float* out_soft;  // idx: output if RASTER else input
   SoftFwdOut kl;
 };
@@ -986,16 +990,227 @@ __global__ void __launch_bounds__(kThreads, 4) soft_tiles_fwd_kernel(const __gri
   extern __shared__ __align__(128) unsigned char soft_smem_raw[];
   SoftSmem& sm = *reinterpret_cast<SoftSmem*>(soft_smem_raw);
   const Scene& s = a.s;
-  const int total = min(*s.band_ctr, s.ntx[0] * s.nty[0] * s.B);
+  const int total = min(a.from_fb ? *s.fb_ctr : *s.band_ctr, s.ntx[0] * s.nty[0] * s.B);
+  const int* list = a.from_fb ? s.fb_list : s.band_list;
   SoftIO io;
   io.out_soft = a.out_soft; io.kl = a.kl; io.grad_soft = nullptr; io.soft = nullptr; io.grad_xy = nullptr;
   for (int w = blockIdx.x; w < total; w += gridDim.x) {
-    const TileCtx c = tile_ctx_from_linear(s, s.band_list[w]);
+    const TileCtx c = tile_ctx_from_linear(s, list[w]);
     __syncthreads();  // previous tile's shared state fully consumed
     load_bin_table(s, c, sm);
     __syncthreads();
     soft_tile_fwd<KLISTS>(s, c, sm, c.in_img && a.idx[c.pix] < 0, a.sigmainv, a.K, !KLISTS && a.cache != 0, io);
   }
+}
+
+// ---------------------------------------------------------------------------
+// Three-kernel soft-mask forward (knum <= 32, hit cache available):
+//   soft_enum_kernel : per silhouette tile, decides WHICH (pixel, face) pairs exist
+//                      (integer work only) and lays them out face-major in the tile's
+//                      cache block, with each pixel's slot list in face order;
+//   soft_eval_kernel : one thread per pair over all tiles — the expensive
+//                      distance / probability, dense and barrier-free;
+//   soft_fold_kernel : each pixel folds its probabilities in face order.
+// Tiles that do not fit the cache go to fb_list and take the single-kernel path.
+constexpr int kEnumK = 32;
+
+struct EnumSmem {
+  unsigned long long list[kSoftCap];
+  unsigned long long sorted[kSoftCap];
+  int cface[kChunk];
+  uint32_t colbits[kChunk / 32][16];
+  uint32_t rowbits[kChunk / 32][16];
+  int cnt_c[kChunk];
+  int off_c[kChunk];
+  uint16_t claim[kThreads][kEnumK];
+  uint8_t apix[kThreads];
+  BinRef bin[2][kMaxLevels];
+  int wcount[kThreads / 32];
+  int nsoft, nent, pool_slot, npairs;
+};
+
+__global__ void __launch_bounds__(kThreads) soft_enum_kernel(const __grid_constant__ FwdArgs a) {
+  __shared__ __align__(128) EnumSmem sm;
+  const Scene& s = a.s;
+  const int K = a.K;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int total = min(*s.band_ctr, s.ntx[0] * s.nty[0] * s.B);
+  const size_t E = (size_t)256 * s.pool_K;
+  for (int w = blockIdx.x; w < total; w += gridDim.x) {
+    const TileCtx c = tile_ctx_from_linear(s, s.band_list[w]);
+    __syncthreads();  // previous tile's shared state fully consumed
+    load_bin_table(s, c, sm);
+    const bool uncovered = c.in_img && a.idx[c.pix] < 0;
+    const unsigned av = __ballot_sync(kFull, uncovered);
+    if (lane == 0) sm.wcount[warp] = __popc(av);
+    __syncthreads();
+    int before = 0, na = 0;
+#pragma unroll
+    for (int q = 0; q < kThreads / 32; ++q) {
+      const int cw = sm.wcount[q];
+      if (q < warp) before += cw;
+      na += cw;
+    }
+    if (na == 0) continue;  // uniform
+    if (uncovered) sm.apix[before + __popc(av & ((1u << lane) - 1u))] = (uint8_t)(c.lx | (c.ly << 4));
+    __syncthreads();
+    const bool active = tid < na;
+    int lx = 0, ly = 0;
+    if (active) { const int p = sm.apix[tid]; lx = p & 15; ly = p >> 4; }
+    int kid = 0;
+    const int maxf = s.first ? (int)(__ldg(s.first + c.b + 1) - c.fbase) : s.F;
+    uint32_t* blk = nullptr;
+    uint16_t* myslots = nullptr;
+    bool first_window = true, cached = true;
+    int lo = -1;
+    while (true) {
+      int hi = 0x7fffffff;
+      int n = soft_collect<false>(s, c, sm, lo, hi);
+      if (n > kSoftCap) {
+        int L = lo + 1, R = maxf - 1;
+        while (L < R) {
+          const int mid = L + (R - L + 1) / 2;
+          if (soft_collect<true>(s, c, sm, lo, mid) <= kSoftCap) L = mid; else R = mid - 1;
+        }
+        hi = L;
+        n = soft_collect<false>(s, c, sm, lo, hi);
+      }
+      if (first_window) {
+        first_window = false;
+        if (tid == 0) {
+          int slot = -1;
+          if (n > 0) {
+            slot = atomicAdd(s.pool_ctr, 1);
+            if (slot >= s.pool_tiles) {   // cache full: single-kernel path + recompute in backward
+              slot = -1;
+              s.fb_list[atomicAdd(s.fb_ctr, 1)] = tile_linear(s, c);
+            }
+          }
+          sm.pool_slot = slot;
+          sm.nent = 0;
+        }
+        __syncthreads();
+        if (sm.pool_slot < 0) { cached = false; break; }  // uniform: nothing to do / handed over
+        blk = s.pool_data + (size_t)sm.pool_slot * 3 * E;
+        myslots = s.pool_slots + ((size_t)sm.pool_slot * kThreads + tid) * kEnumK;
+      }
+      for (int j = tid; j < n; j += kThreads) {
+        const unsigned long long key = sm.list[j];
+        int rank = 0;
+        for (int i = 0; i < n; ++i) rank += (sm.list[i] < key) ? 1 : 0;
+        sm.sorted[rank] = key;
+      }
+      __syncthreads();
+      bool all_done = false;
+      for (int c0 = 0; c0 < n && !all_done; c0 += kChunk) {
+        const int cn = min(kChunk, n - c0);
+        const int ngroups = (cn + 31) >> 5;
+        uint32_t m = 0;
+        if (tid < cn) {
+          const unsigned long long key = sm.sorted[c0 + tid];
+          m = (uint32_t)key;
+          sm.cface[tid] = (int)(key >> 32);
+        }
+        if (warp < ngroups) store_bit_matrix(m, sm.colbits, sm.rowbits, warp);
+        sm.cnt_c[tid] = 0;
+        __syncthreads();
+        // every uncovered pixel claims ALL its remaining faces of this chunk (index order, <= knum)
+        int took = 0;
+        if (active) {
+          for (int g = 0; g < ngroups && kid + took < K; ++g) {
+            uint32_t bits = sm.colbits[g][lx] & sm.rowbits[g][ly];
+            while (bits && kid + took < K) {
+              const int j = (g << 5) + __ffs(bits) - 1;
+              bits &= bits - 1;
+              const int pos = atomicAdd(&sm.cnt_c[j], 1);
+              sm.claim[tid][took] = (uint16_t)(j | (pos << 8));
+              ++took;
+            }
+          }
+        }
+        __syncthreads();
+        if (warp == 0) {  // face-major offsets
+          int v[8], sum = 0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const int j = lane * 8 + i; v[i] = j < cn ? sm.cnt_c[j] : 0; sum += v[i]; }
+          int x = sum;
+#pragma unroll
+          for (int d = 1; d < 32; d <<= 1) { const int y = __shfl_up_sync(kFull, x, d); if (lane >= d) x += y; }
+          int run = x - sum;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) { const int j = lane * 8 + i; if (j < cn) sm.off_c[j] = run; run += v[i]; }
+          if (lane == 31) sm.npairs = x;
+        }
+        __syncthreads();
+        const int ebase = sm.nent;
+        for (int i = 0; i < took; ++i) {
+          const int cl = sm.claim[tid][i];
+          const int j = cl & 0xff;
+          const int slot = ebase + sm.off_c[j] + (cl >> 8);
+          blk[slot] = (uint32_t)sm.cface[j];
+          blk[2 * E + slot] = (uint32_t)lx | ((uint32_t)ly << 4);
+          myslots[kid + i] = (uint16_t)slot;
+        }
+        kid += took;
+        all_done = __syncthreads_and(!active || kid >= K);
+        if (tid == 0) sm.nent = ebase + sm.npairs;
+      }
+      if (hi == 0x7fffffff || all_done) break;
+      lo = hi;
+    }
+    if (cached && blk != nullptr) {
+      __syncthreads();
+      s.pool_aux[(size_t)sm.pool_slot * kThreads + tid] =
+          active ? ((uint32_t)(lx | (ly << 4)) | ((uint32_t)kid << 8)) : 0u;
+      if (tid == 0) {
+        s.pool_hdr[sm.pool_slot] = make_int4(c.b, c.tx, c.ty, sm.nent);
+        s.pool_na[sm.pool_slot] = na;
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) soft_eval_kernel(const __grid_constant__ FwdArgs a) {
+  const Scene& s = a.s;
+  const int used = min(*s.pool_ctr, s.pool_tiles);
+  if ((int)blockIdx.x >= used) return;
+  const int4 h = s.pool_hdr[blockIdx.x];  // b, tx, ty, hits
+  const size_t E = (size_t)256 * s.pool_K;
+  uint32_t* blk = s.pool_data + (size_t)blockIdx.x * 3 * E;
+  const int64_t fbase = view_fbase(s, h.x);
+  const int tid = threadIdx.x;
+  uint32_t nface = 0, nmeta = 0;
+  if (tid < h.w) { nface = blk[tid]; nmeta = blk[2 * E + tid]; }
+  for (int t = tid; t < h.w; t += kThreads) {
+    const uint32_t face = nface, meta = nmeta;
+    if (t + kThreads < h.w) { nface = blk[t + kThreads]; nmeta = blk[2 * E + t + kThreads]; }
+    const int px = h.y * kTile + (int)(meta & 15u), py = h.z * kTile + (int)((meta >> 4) & 15u);
+    float v[6];
+    load_xy(s, fbase + (int)face, v);
+    int edgeid;
+    const float d2 = soft_min_dist(pix_x(s.grid, px), pix_y(s.grid, py), v, s.multiplier, edgeid);
+    const float prob = soft_prob(d2, a.sigmainv, s.multiplier);
+    blk[E + t] = __float_as_uint(prob);
+    blk[2 * E + t] = meta | ((uint32_t)(edgeid + 1) << 8);
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) soft_fold_kernel(const __grid_constant__ FwdArgs a) {
+  const Scene& s = a.s;
+  const int used = min(*s.pool_ctr, s.pool_tiles);
+  if ((int)blockIdx.x >= used) return;
+  const int tid = threadIdx.x;
+  if (tid >= s.pool_na[blockIdx.x]) return;
+  const int4 h = s.pool_hdr[blockIdx.x];
+  const size_t E = (size_t)256 * s.pool_K;
+  const uint32_t* blk = s.pool_data + (size_t)blockIdx.x * 3 * E;
+  const uint32_t aux = s.pool_aux[(size_t)blockIdx.x * kThreads + tid];
+  const uint16_t* myslots = s.pool_slots + ((size_t)blockIdx.x * kThreads + tid) * kEnumK;
+  const int cnt = (int)(aux >> 8);
+  float allprob = 1.0f;
+  for (int i = 0; i < cnt; ++i) allprob = soft_accumulate(allprob, __uint_as_float(blk[E + myslots[i]]));
+  const int px = h.y * kTile + (int)(aux & 15u), py = h.z * kTile + (int)((aux >> 4) & 15u);
+  a.out_soft[((int64_t)h.x * s.H + py) * s.W + px] = soft_finish(allprob);
 }
 
 // ---------------------------------------------------------------------------
@@ -1274,7 +1489,12 @@ Layout layout_for(int B, int64_t NF, int H, int W) {
   return L;
 }
 
-size_t pool_block_bytes(int K) { return sizeof(int4) + (size_t)3 * 256 * (size_t)K * sizeof(uint32_t); }
+size_t pool_aux_bytes(int K) {  // per-tile extras of the 3-kernel forward
+  return K <= kEnumK ? sizeof(int) + 256 * sizeof(uint32_t) + (size_t)256 * kEnumK * sizeof(uint16_t) : 0;
+}
+size_t pool_block_bytes(int K) {
+  return sizeof(int4) + pool_aux_bytes(K) + (size_t)3 * 256 * (size_t)K * sizeof(uint32_t);
+}
 
 int check_dims(int B, int64_t NF, int H, int W) {
   if (B <= 0 || H <= 0 || W <= 0 || NF < 0) return DIBR_B200_EINVAL;
@@ -1314,17 +1534,30 @@ int setup_scene(Scene& s, int B, int64_t NF, int F, int H, int W, float multipli
   s.fb_list = (int*)p; s.band_list = (int*)(p + Lo.mode / 2); p += Lo.mode;
   s.entries = (int4*)p; p += Lo.ent;
   s.pool_tiles = 0; s.pool_K = knum > 0 ? knum : 1; s.pool_hdr = nullptr; s.pool_data = nullptr;
+  s.pool_na = nullptr; s.pool_aux = nullptr; s.pool_slots = nullptr;
   if (knum > 0) {
     const size_t left = (size_t)(end - p);
     const size_t data = (size_t)3 * 256 * (size_t)knum * sizeof(uint32_t);
-    size_t n = left / (data + sizeof(int4));
+    const bool aux = knum <= kEnumK;
+    auto need = [&](size_t n) {
+      size_t b = align_up(n * sizeof(int4), 256) + n * data;
+      if (aux) b += align_up(n * sizeof(int), 256) + n * 256 * sizeof(uint32_t) +
+                    align_up(n * 256 * kEnumK * sizeof(uint16_t), 256);
+      return b;
+    };
+    size_t n = left / pool_block_bytes(knum);
     const size_t tiles = (size_t)s.ntx[0] * s.nty[0] * B;
     if (n > tiles) n = tiles;
-    while (n > 0 && align_up(n * sizeof(int4), 256) + n * data > left) --n;
+    while (n > 0 && need(n) > left) --n;
     if (n > 0) {
       s.pool_tiles = (int)n;
-      s.pool_hdr = (int4*)p;
-      s.pool_data = (uint32_t*)(p + align_up(n * sizeof(int4), 256));
+      s.pool_hdr = (int4*)p; p += align_up(n * sizeof(int4), 256);
+      if (aux) {
+        s.pool_na = (int*)p; p += align_up(n * sizeof(int), 256);
+        s.pool_aux = (uint32_t*)p; p += n * 256 * sizeof(uint32_t);
+        s.pool_slots = (uint16_t*)p; p += align_up(n * 256 * kEnumK * sizeof(uint16_t), 256);
+      }
+      s.pool_data = (uint32_t*)p;
     }
   }
   return 0;
@@ -1360,13 +1593,25 @@ unsigned persistent_grid(const Scene& s, Kernel kernel, size_t dyn_smem = 0) {
 }
 
 template <bool R, bool S, bool K>
-void launch_fwd(const FwdArgs& a, cudaStream_t st) {
+void launch_fwd(const FwdArgs& a0, cudaStream_t st) {
+  FwdArgs a = a0;
+  a.from_fb = 0;
   dibr_tile_fwd_kernel<R, S, K><<<tile_grid(a.s), kThreads, 0, st>>>(a);
   if (S) {
     cudaFuncSetAttribute(soft_tiles_fwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(SoftSmem));
-    soft_tiles_fwd_kernel<K><<<persistent_grid(a.s, soft_tiles_fwd_kernel<K>, sizeof(SoftSmem)), kThreads,
-                               sizeof(SoftSmem), st>>>(a);
+    const unsigned g1 = persistent_grid(a.s, soft_tiles_fwd_kernel<K>, sizeof(SoftSmem));
+    if (!K && a.cache && a.s.pool_tiles > 0 && a.s.pool_slots != nullptr) {
+      // enumerate -> evaluate densely -> fold; tiles beyond the cache take the single-kernel path
+      soft_enum_kernel<<<persistent_grid(a.s, soft_enum_kernel), kThreads, 0, st>>>(a);
+      soft_eval_kernel<<<(unsigned)a.s.pool_tiles, kThreads, 0, st>>>(a);
+      soft_fold_kernel<<<(unsigned)a.s.pool_tiles, kThreads, 0, st>>>(a);
+      a.from_fb = 1;
+      a.cache = 0;
+      soft_tiles_fwd_kernel<K><<<g1, kThreads, sizeof(SoftSmem), st>>>(a);
+    } else {
+      soft_tiles_fwd_kernel<K><<<g1, kThreads, sizeof(SoftSmem), st>>>(a);
+    }
   }
 }
 

@@ -53,7 +53,7 @@ def workspace(batch, total_faces, height, width, device, knum=0):
     if knum > 0:
         tiles = batch * ((height + 15) // 16) * ((width + 15) // 16)
         want = max(CACHE_MIN_TILES, int(tiles * CACHE_TILE_FRACTION))
-        want = min(tiles, want, max(1, CACHE_MAX_BYTES // (3072 * knum + 16)))
+        want = min(tiles, want, max(1, CACHE_MAX_BYTES // (3072 * knum + 17500)))
         n = _lib.lib().dibr_b200_workspace_bytes_cached(batch, total_faces, height, width, knum, want)
     else:
         n = _lib.lib().dibr_b200_workspace_bytes(batch, total_faces, height, width)
