@@ -36,6 +36,7 @@ constexpr int kSoftCap = 1024;  // soft-mask candidates sorted per pass
 constexpr int kRound = 12;      // hits a pixel contributes to one pair round
 constexpr int kPairCap = kThreads * kRound;
 constexpr unsigned kFull = 0xffffffffu;
+constexpr int kBandRec = 24;    // ints per record of the soft-mask work list
 
 // ---------------------------------------------------------------------------
 // Scene description shared by all kernels (passed by value).
@@ -71,8 +72,11 @@ struct Scene {
   uint16_t* pool_slots;   // [pool_tiles][256][32] its hit slots, face order      } 3-kernel forward
   int* fb_ctr;            // [1] tiles whose hits did not fit the cache (recomputed in backward)
   int* fb_list;           // [B*nty*ntx] their linear tile ids
+  int* tile_cnt;          // [B*nty*ntx] enlarged face rectangles over each 16x16 tile (count pass)
+  int* view_flag;         // [B] the view has an enlarged rectangle too big to count per tile
   int* band_ctr;          // [1] tiles with uncovered pixels under some enlarged face rectangle
-  int* band_list;         // [B*nty*ntx] their linear tile ids (work list of the soft-mask kernel)
+  int* band_list;         // [B*nty*ntx][kBandRec] work list of the soft-mask kernels: per tile
+                          //   {linear tile id, 8 x uncovered-pixel ballot, 6 x (large-bin offset, size), pad}
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -205,7 +209,19 @@ __global__ void __launch_bounds__(256) bin_faces_kernel(Scene s, int sets) {
       xmax = fadd(fmaxf(fmaxf(v[0], v[2]), v[4]), s.margin);
       ymax = fadd(fmaxf(fmaxf(v[1], v[3]), v[5]), s.margin);
     }
-    emit_rect<FILL>(s, 1, b, fbase, f, bbox_to_rect(s.grid, xmin, ymin, xmax, ymax));
+    const PixRect r = bbox_to_rect(s.grid, xmin, ymin, xmax, ymax);
+    emit_rect<FILL>(s, 1, b, fbase, f, r);
+    if (!FILL && r.x_hi > r.x_lo && r.y_hi > r.y_lo) {
+      // which 16x16 tiles can see this face in the soft mask (filters the soft-mask work list)
+      const int tx0 = r.x_lo >> 4, tx1 = (r.x_hi - 1) >> 4, ty0 = r.y_lo >> 4, ty1 = (r.y_hi - 1) >> 4;
+      if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= 64) {
+        for (int ty = ty0; ty <= ty1; ++ty)
+          for (int tx = tx0; tx <= tx1; ++tx)
+            atomicAdd(s.tile_cnt + ((size_t)b * s.nty[0] + ty) * s.ntx[0] + tx, 1);
+      } else {
+        atomicOr(s.view_flag + b, 1);
+      }
+    }
   }
 }
 
@@ -336,6 +352,7 @@ struct RasterSmem {
   unsigned long long bar[2];
   BinRef bin[2][kMaxLevels];
   int any_uncovered, warps_done;
+  unsigned uncmask[kThreads / 32];
 };
 
 // Transposes the tile-local rectangle masks of the 32 candidates held by a warp
@@ -884,6 +901,18 @@ __device__ __forceinline__ void soft_tile_fwd(const Scene& s, const TileCtx& c, 
   if (blk != nullptr && tid == 0) s.pool_hdr[sm.pool_slot] = make_int4(c.b, c.tx, c.ty, sm.nent);
 }
 
+// Large-set bin table of a tile from its work-list record (threads 0..5 write it).
+template <typename SM>
+__device__ __forceinline__ void bins_from_record(const Scene& s, const int* rec, int64_t fbase, SM& sm) {
+  const int tid = threadIdx.x;
+  if (tid < kMaxLevels) {
+    BinRef r;
+    r.n = __ldg(rec + 10 + 2 * tid);
+    r.ptr = s.entries + (size_t)4 * s.NF + 4 * fbase + __ldg(rec + 9 + 2 * tid);
+    sm.bin[1][tid] = r;
+  }
+}
+
 __device__ __forceinline__ TileCtx tile_ctx_from_linear(const Scene& s, int t) {
   TileCtx c;
   const int tiles_xy = s.ntx[0] * s.nty[0];
@@ -973,12 +1002,23 @@ __global__ void __launch_bounds__(kThreads, 6) dibr_tile_fwd_kernel(const __grid
     // no CTA barrier: warps retire independently; the last one to finish files the tile
     const unsigned wv = __ballot_sync(kFull, uncovered);
     if ((tid & 31) == 0) {
+      sm.uncmask[tid >> 5] = wv;
       if (wv) atomicOr(&sm.any_uncovered, 1);
       __threadfence_block();
       if (atomicAdd(&sm.warps_done, 1) == kThreads / 32 - 1 && atomicOr(&sm.any_uncovered, 0)) {
-        int nlarge = 0;
-        for (int l = 0; l < kMaxLevels; ++l) nlarge += sm.bin[1][l].n;
-        if (nlarge > 0) s.band_list[atomicAdd(s.band_ctr, 1)] = tile_linear(s, c);
+        const int nlarge = __ldg(s.tile_cnt + tile_linear(s, c)) + __ldg(s.view_flag + c.b);
+        if (nlarge > 0) {
+          // work-list record: everything the soft-mask kernels need to start without
+          // re-reading face_idx or the bin tables
+          int* rec = s.band_list + (size_t)atomicAdd(s.band_ctr, 1) * kBandRec;
+          const int4* ebase = s.entries + (size_t)4 * s.NF + 4 * c.fbase;
+          rec[0] = tile_linear(s, c);
+          for (int q = 0; q < kThreads / 32; ++q) rec[1 + q] = (int)atomicOr(&sm.uncmask[q], 0u);
+          for (int l = 0; l < kMaxLevels; ++l) {
+            rec[9 + 2 * l] = sm.bin[1][l].n > 0 ? (int)(sm.bin[1][l].ptr - ebase) : 0;
+            rec[10 + 2 * l] = sm.bin[1][l].n;
+          }
+        }
       }
     }
   }
@@ -991,11 +1031,10 @@ __global__ void __launch_bounds__(kThreads, 4) soft_tiles_fwd_kernel(const __gri
   SoftSmem& sm = *reinterpret_cast<SoftSmem*>(soft_smem_raw);
   const Scene& s = a.s;
   const int total = min(a.from_fb ? *s.fb_ctr : *s.band_ctr, s.ntx[0] * s.nty[0] * s.B);
-  const int* list = a.from_fb ? s.fb_list : s.band_list;
   SoftIO io;
   io.out_soft = a.out_soft; io.kl = a.kl; io.grad_soft = nullptr; io.soft = nullptr; io.grad_xy = nullptr;
   for (int w = blockIdx.x; w < total; w += gridDim.x) {
-    const TileCtx c = tile_ctx_from_linear(s, list[w]);
+    const TileCtx c = tile_ctx_from_linear(s, a.from_fb ? s.fb_list[w] : s.band_list[(size_t)w * kBandRec]);
     __syncthreads();  // previous tile's shared state fully consumed
     load_bin_table(s, c, sm);
     __syncthreads();
@@ -1037,26 +1076,25 @@ __global__ void __launch_bounds__(kThreads) soft_enum_kernel(const __grid_consta
   const int total = min(*s.band_ctr, s.ntx[0] * s.nty[0] * s.B);
   const size_t E = (size_t)256 * s.pool_K;
   for (int w = blockIdx.x; w < total; w += gridDim.x) {
-    const TileCtx c = tile_ctx_from_linear(s, s.band_list[w]);
-    __syncthreads();  // previous tile's shared state fully consumed
-    load_bin_table(s, c, sm);
-    const bool uncovered = c.in_img && a.idx[c.pix] < 0;
-    const unsigned av = __ballot_sync(kFull, uncovered);
-    if (lane == 0) sm.wcount[warp] = __popc(av);
-    __syncthreads();
+    // the work-list record carries the tile id, the uncovered-pixel ballots of the
+    // rasterizer's 8 warps and the tile's large-bin table: one load latency, no
+    // face_idx re-read, no barrier for the compaction
+    const int* rec = s.band_list + (size_t)w * kBandRec;
+    const TileCtx c = tile_ctx_from_linear(s, __ldg(rec));
+    unsigned mymask = 0;
     int before = 0, na = 0;
 #pragma unroll
     for (int q = 0; q < kThreads / 32; ++q) {
-      const int cw = sm.wcount[q];
-      if (q < warp) before += cw;
-      na += cw;
+      const unsigned mq = (unsigned)__ldg(rec + 1 + q);
+      if (q < warp) before += __popc(mq);
+      if (q == warp) mymask = mq;
+      na += __popc(mq);
     }
-    if (na == 0) continue;  // uniform
-    if (uncovered) sm.apix[before + __popc(av & ((1u << lane) - 1u))] = (uint8_t)(c.lx | (c.ly << 4));
-    __syncthreads();
+    __syncthreads();  // previous tile's shared state fully consumed
+    bins_from_record(s, rec, c.fbase, sm);
+    if ((mymask >> lane) & 1u) sm.apix[before + __popc(mymask & ((1u << lane) - 1u))] = (uint8_t)(c.lx | (c.ly << 4));
     const bool active = tid < na;
     int lx = 0, ly = 0;
-    if (active) { const int p = sm.apix[tid]; lx = p & 15; ly = p >> 4; }
     int kid = 0;
     const int maxf = s.first ? (int)(__ldg(s.first + c.b + 1) - c.fbase) : s.F;
     uint32_t* blk = nullptr;
@@ -1066,6 +1104,7 @@ __global__ void __launch_bounds__(kThreads) soft_enum_kernel(const __grid_consta
     while (true) {
       int hi = 0x7fffffff;
       int n = soft_collect<false>(s, c, sm, lo, hi);
+      if (first_window && active) { const int p = sm.apix[tid]; lx = p & 15; ly = p >> 4; }
       if (n > kSoftCap) {
         int L = lo + 1, R = maxf - 1;
         while (L < R) {
@@ -1075,24 +1114,20 @@ __global__ void __launch_bounds__(kThreads) soft_enum_kernel(const __grid_consta
         hi = L;
         n = soft_collect<false>(s, c, sm, lo, hi);
       }
+      const bool alloc = first_window;
       if (first_window) {
         first_window = false;
+        if (n == 0) { cached = false; break; }  // uncovered pixels, but no face near them: soft stays 0
+        // cache block: one atomic, its round trip hidden behind the sort below
         if (tid == 0) {
-          int slot = -1;
-          if (n > 0) {
-            slot = atomicAdd(s.pool_ctr, 1);
-            if (slot >= s.pool_tiles) {   // cache full: single-kernel path + recompute in backward
-              slot = -1;
-              s.fb_list[atomicAdd(s.fb_ctr, 1)] = tile_linear(s, c);
-            }
+          int slot = atomicAdd(s.pool_ctr, 1);
+          if (slot >= s.pool_tiles) {   // cache full: single-kernel path + recompute in backward
+            slot = -1;
+            s.fb_list[atomicAdd(s.fb_ctr, 1)] = tile_linear(s, c);
           }
           sm.pool_slot = slot;
           sm.nent = 0;
         }
-        __syncthreads();
-        if (sm.pool_slot < 0) { cached = false; break; }  // uniform: nothing to do / handed over
-        blk = s.pool_data + (size_t)sm.pool_slot * 3 * E;
-        myslots = s.pool_slots + ((size_t)sm.pool_slot * kThreads + tid) * kEnumK;
       }
       for (int j = tid; j < n; j += kThreads) {
         const unsigned long long key = sm.list[j];
@@ -1101,6 +1136,11 @@ __global__ void __launch_bounds__(kThreads) soft_enum_kernel(const __grid_consta
         sm.sorted[rank] = key;
       }
       __syncthreads();
+      if (alloc) {
+        if (sm.pool_slot < 0) { cached = false; break; }  // uniform: handed over to the single-kernel path
+        blk = s.pool_data + (size_t)sm.pool_slot * 3 * E;
+        myslots = s.pool_slots + ((size_t)sm.pool_slot * kThreads + tid) * kEnumK;
+      }
       bool all_done = false;
       for (int c0 = 0; c0 < n && !all_done; c0 += kChunk) {
         const int cn = min(kChunk, n - c0);
@@ -1158,7 +1198,7 @@ __global__ void __launch_bounds__(kThreads) soft_enum_kernel(const __grid_consta
       if (hi == 0x7fffffff || all_done) break;
       lo = hi;
     }
-    if (cached && blk != nullptr) {
+    if (cached) {
       __syncthreads();
       s.pool_aux[(size_t)sm.pool_slot * kThreads + tid] =
           active ? ((uint32_t)(lx | (ly << 4)) | ((uint32_t)kid << 8)) : 0u;
@@ -1193,24 +1233,17 @@ __global__ void __launch_bounds__(kThreads) soft_eval_kernel(const __grid_consta
     blk[E + t] = __float_as_uint(prob);
     blk[2 * E + t] = meta | ((uint32_t)(edgeid + 1) << 8);
   }
-}
-
-__global__ void __launch_bounds__(kThreads) soft_fold_kernel(const __grid_constant__ FwdArgs a) {
-  const Scene& s = a.s;
-  const int used = min(*s.pool_ctr, s.pool_tiles);
-  if ((int)blockIdx.x >= used) return;
-  const int tid = threadIdx.x;
+  // fold: each uncovered pixel multiplies its probabilities in face order
+  // (dibr_soft_mask_cuda.cu:174-182); the tile's pairs were all evaluated by this CTA
+  __syncthreads();
   if (tid >= s.pool_na[blockIdx.x]) return;
-  const int4 h = s.pool_hdr[blockIdx.x];
-  const size_t E = (size_t)256 * s.pool_K;
-  const uint32_t* blk = s.pool_data + (size_t)blockIdx.x * 3 * E;
   const uint32_t aux = s.pool_aux[(size_t)blockIdx.x * kThreads + tid];
   const uint16_t* myslots = s.pool_slots + ((size_t)blockIdx.x * kThreads + tid) * kEnumK;
   const int cnt = (int)(aux >> 8);
   float allprob = 1.0f;
   for (int i = 0; i < cnt; ++i) allprob = soft_accumulate(allprob, __uint_as_float(blk[E + myslots[i]]));
-  const int px = h.y * kTile + (int)(aux & 15u), py = h.z * kTile + (int)((aux >> 4) & 15u);
-  a.out_soft[((int64_t)h.x * s.H + py) * s.W + px] = soft_finish(allprob);
+  const int fx = h.y * kTile + (int)(aux & 15u), fy = h.z * kTile + (int)((aux >> 4) & 15u);
+  a.out_soft[((int64_t)h.x * s.H + fy) * s.W + fx] = soft_finish(allprob);
 }
 
 // ---------------------------------------------------------------------------
@@ -1481,9 +1514,9 @@ struct Layout { size_t cnt, off, mode, ent, base; };
 Layout layout_for(int B, int64_t NF, int H, int W) {
   Layout L;
   const size_t tiles = (size_t)((W + kTile - 1) / kTile) * ((H + kTile - 1) / kTile) * B;
-  L.cnt = align_up(((size_t)2 * B * bins_per_view(H, W) + 3) * sizeof(int), 256);
+  L.cnt = align_up(((size_t)2 * B * bins_per_view(H, W) + 3 + B + tiles) * sizeof(int), 256);
   L.off = align_up((size_t)2 * B * bins_per_view(H, W) * sizeof(int), 256);
-  L.mode = 2 * align_up(tiles * sizeof(int), 256);
+  L.mode = align_up(tiles * sizeof(int), 256) + align_up(tiles * kBandRec * sizeof(int), 256);
   L.ent = align_up((size_t)2 * 4 * (size_t)(NF > 0 ? NF : 1) * sizeof(int4), 256);
   L.base = L.cnt + L.off + L.mode + L.ent + 256;
   return L;
@@ -1529,9 +1562,13 @@ int setup_scene(Scene& s, int B, int64_t NF, int F, int H, int W, float multipli
   s.pool_ctr = s.cnt + (size_t)2 * B * nb;
   s.fb_ctr = s.pool_ctr + 1;
   s.band_ctr = s.pool_ctr + 2;
+  s.view_flag = s.pool_ctr + 3;
+  s.tile_cnt = s.view_flag + B;
   p += Lo.cnt;
   s.off = (int*)p; p += Lo.off;
-  s.fb_list = (int*)p; s.band_list = (int*)(p + Lo.mode / 2); p += Lo.mode;
+  s.fb_list = (int*)p;
+  s.band_list = (int*)(p + align_up((size_t)s.ntx[0] * s.nty[0] * B * sizeof(int), 256));
+  p += Lo.mode;
   s.entries = (int4*)p; p += Lo.ent;
   s.pool_tiles = 0; s.pool_K = knum > 0 ? knum : 1; s.pool_hdr = nullptr; s.pool_data = nullptr;
   s.pool_na = nullptr; s.pool_aux = nullptr; s.pool_slots = nullptr;
@@ -1564,7 +1601,8 @@ int setup_scene(Scene& s, int B, int64_t NF, int F, int H, int W, float multipli
 }
 
 int build_bins(const Scene& s, int sets, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(s.cnt, 0, ((size_t)2 * s.B * s.NB + 3) * sizeof(int), st);
+  const size_t zero_ints = (size_t)2 * s.B * s.NB + 3 + s.B + (size_t)s.ntx[0] * s.nty[0] * s.B;
+  cudaError_t e = cudaMemsetAsync(s.cnt, 0, zero_ints * sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
   if (s.NF > 0) {
     const unsigned blocks = (unsigned)((s.NF + 255) / 256);
@@ -1605,7 +1643,6 @@ void launch_fwd(const FwdArgs& a0, cudaStream_t st) {
       // enumerate -> evaluate densely -> fold; tiles beyond the cache take the single-kernel path
       soft_enum_kernel<<<persistent_grid(a.s, soft_enum_kernel), kThreads, 0, st>>>(a);
       soft_eval_kernel<<<(unsigned)a.s.pool_tiles, kThreads, 0, st>>>(a);
-      soft_fold_kernel<<<(unsigned)a.s.pool_tiles, kThreads, 0, st>>>(a);
       a.from_fb = 1;
       a.cache = 0;
       soft_tiles_fwd_kernel<K><<<g1, kThreads, sizeof(SoftSmem), st>>>(a);
