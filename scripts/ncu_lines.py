@@ -21,10 +21,10 @@ def main():
     rep, kre, lib = sys.argv[1:4]
     topn = int(sys.argv[4]) if len(sys.argv) > 4 else 40
     out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass",
-                          "--kernel-name", f"regex:{kre}"], capture_output=True, text=True).stdout
+                          ], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(out)))
     # first kernel instance only
-    start = next(i for i, r in enumerate(rows) if r and r[0] == "Kernel Name")
+    start = next(i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and re.search(kre, r[1]))
     kname = rows[start][1]
     hdr = rows[start + 1]
     body = []

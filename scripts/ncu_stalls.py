@@ -3,9 +3,10 @@
 import collections, csv, io, subprocess, sys
 rep, kern = sys.argv[1:3]
 out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv", "--print-source", "sass",
-                      "--kernel-name", f"regex:{kern}"], capture_output=True, text=True).stdout
+                      ], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
-start = next(i for i, r in enumerate(rows) if r and r[0] == "Kernel Name")
+import re
+start = next(i for i, r in enumerate(rows) if r and r[0] == "Kernel Name" and re.search(kern, r[1]))
 hdr = rows[start + 1]; ci = {h: i for i, h in enumerate(hdr)}
 stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 tot = collections.Counter(); opcount = collections.Counter(); opsamp = collections.Counter()
