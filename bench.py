@@ -366,10 +366,21 @@ def run_ours(args):
     peak, peak_src = peaks()
     A = algorithmic_bytes(B, F, H, W, D)
     ach = A["bwd_raster"] / (raster_bwd_ms * 1e-3) / 1e9
+    traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel (ncu --set full)
+    try:
+        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_kernels.json")))
+        for name, e in prof.items():
+            if "raster_bwd_kernel" in name and args.workload == "c4_shard":
+                traffic = e.get("dram_traffic_bytes")
+    except Exception:
+        traffic = None
     roofline = {
-        "kernel": "raster_bwd_kernel<3> (+2 output memsets) via dibr_b200_rasterize_backward",
+        "kernel": "raster_bwd_kernel<3> (+2 output memsets) via dibr_b200_rasterize_backward — the "
+                  "backward scatter BASELINE.json grades; the largest single kernel is "
+                  "dibr_tile_fwd_kernel (see profiles/r1_kernels.md)",
         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-        "traffic": None, "peak_source": peak_src,
+        "traffic": traffic, "traffic_source": "profiles/r1_kernels.json (ncu --set full, c4_shard)",
+        "peak_source": peak_src,
         "algorithmic_bytes_per_launch": A["bwd_raster"], "ms_per_launch": raster_bwd_ms,
         "phases": {
             "forward_ms": fwd_ms, "backward_ms": bwd_ms,
@@ -395,7 +406,7 @@ def run_ours(args):
                 "api": "kaolin_b200.render.mesh.dibr_rasterization + autograd, pinned host buffers; "
                        "uploads/downloads double-buffered on side streams",
                 "host_wall_ms_per_step": wall_ms / args.steps},
-        "gpu_launches": 7 * args.steps,
+        "gpu_launches": 10 * args.steps,
         "roofline": roofline,
         "triangle_pixel_tests_per_s": {
             "brute_force_equivalent": float(B) * H * W * F * 0.5 / (fwd_ms * 1e-3),

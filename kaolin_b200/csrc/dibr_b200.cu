@@ -5,19 +5,25 @@
 //   kaolin/csrc/render/mesh/dibr_soft_mask_cuda.cu  (forward :27-184, backward :230-353)
 //   kaolin/render/mesh/rasterization.py:273-371, kaolin/render/mesh/dibr.py:29-73
 //
-// Pipeline (forward):  bin_faces<count> -> scan_bins -> bin_faces<fill> -> tile kernel
+// Pipeline (forward):
+//   bin_faces<count> -> scan_bins -> bin_faces<fill> -> dibr_tile_fwd_kernel
+//   -> soft_enum_kernel -> soft_eval_kernel (-> soft_tiles_fwd_kernel for leftovers)
 //   * every face is turned into the exact integer pixel rectangle of the
 //     reference's float bbox test and inserted (<= 4 entries) into the finest
 //     level of a 16/64/256/... px bin pyramid where it spans <= 2x2 bins;
 //   * one CTA per 16x16 screen tile streams the (<= 6) bins above it into
 //     shared memory with TMA bulk copies (cp.async.bulk + mbarrier, double
-//     buffered), culls them against the tile, stages the surviving face records
-//     in shared memory and lets each thread (one pixel) walk them;
-//   * uncovered pixels then walk the "large" (boxlen-enlarged) bins in ascending
-//     face order (the reference keeps the FIRST knum faces by index).
+//     buffered), culls them against the tile, stages the surviving face records,
+//     transposes their rectangle masks into per-column/row candidate bit words and
+//     lets each thread (one pixel) walk exactly its own rectangle hits;
+//   * tiles with uncovered pixels under an enlarged (boxlen) rectangle are filed in
+//     a work list; for them the first knum faces by index of every uncovered pixel
+//     are enumerated (integer work), evaluated densely — one thread per
+//     (pixel, face) pair — and folded per pixel in face order.  The pairs stay in a
+//     per-tile cache block for the backward pass.
 // Backward: a pixel-parallel scatter with warp-level segmented reduction keyed
-// on the face id (rasterize branch) and a tile kernel that recomputes the first-K
-// neighbour walk instead of storing 13*K bytes per pixel (soft-mask branch).
+// on the face id (rasterize branch) and a dense stream over the cached pairs
+// (soft-mask branch; tiles outside the cache are recomputed).
 #include <cuda_runtime.h>
 #include <stdint.h>
 
