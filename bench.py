@@ -33,6 +33,7 @@ WORKLOADS = {
     "c4_shard": (32, 5, 1024, 1024, 3),
     "c2": (8, 4, 256, 256, 3),
     "c3": (64, 5, 512, 512, 3),
+    "c5": (8, 8, 2048, 2048, 3),        # configs[4]: one 1.3 M-triangle mesh, 8 views
     "tiny": (2, 3, 128, 128, 3),
 }
 SIGMAINV, BOXLEN, KNUM, MULT, EPS = 7000.0, 0.02, 30, 1000.0, 1e-8
@@ -120,7 +121,7 @@ class ClockSampler:
 def make_scene(workload, rank):
     from kaolin_b200 import synthetic
     B, level, H, W, D = WORKLOADS[workload]
-    fvz, fvi, fnz = synthetic.icosphere_views(B, level, seed=1234 + 17 * rank)
+    fvz, fvi, fnz = synthetic.icosphere_views(B, level, seed=1234 + 17 * rank, same_mesh=(level >= 8))
     ff = synthetic.random_features(B, fvz.shape[1], D, seed=99 + rank)
     return B, fvz.shape[1], H, W, D, fvz, fvi, fnz, ff
 

@@ -502,7 +502,67 @@ __device__ __forceinline__ int soft_collect(const Scene& s, const TileCtx& c, SM
     }
   }
   __syncthreads();
-  return sm.nsoft;
+  const int n = sm.nsoft;
+  __syncthreads();  // everyone has read the count before a following call resets it
+  return n;
+}
+
+// Collects the tile's soft-mask candidates with face index in (lo, hi] into sm.list.
+// Normally hi = INT_MAX takes everything; when more than kSoftCap faces remain
+// (sub-pixel triangles) a prefix window in index order is taken instead: its upper end
+// is guessed from the average index density and halved until it fits (1-3 counting
+// passes), the caller continues with lo = hi until every pixel has its knum faces.
+template <typename SM>
+__device__ __forceinline__ int soft_window(const Scene& s, const TileCtx& c, SM& sm, int lo, int maxf, int& hi) {
+  hi = 0x7fffffff;
+  int n = soft_collect<false>(s, c, sm, lo, hi);
+  if (n > kSoftCap) {
+    const int span = maxf - 1 - lo;  // indices lo+1 .. maxf-1
+    int width = (int)(((long long)span * kSoftCap * 3) / ((long long)n * 4));
+    if (width < 1) width = 1;
+    while (true) {
+      hi = lo + width;
+      if (soft_collect<true>(s, c, sm, lo, hi) <= kSoftCap || width == 1) break;
+      width = width > 1 ? width / 2 : 1;
+    }
+    n = soft_collect<false>(s, c, sm, lo, hi);
+  }
+  return n;
+}
+
+// Sorts sm.list[0..n) by face index into sm.sorted (keys are unique: a face lives in one
+// level and a tile reads one bin per level).  Small lists (the usual case) use a rank
+// sort, n^2/256 compares per thread and one barrier; big lists (sub-pixel triangles,
+// up to kSoftCap) a shared-memory bitonic network, log^2(n) barriers.  Ends with a barrier.
+template <typename SM>
+__device__ __forceinline__ void soft_sort(SM& sm, int n) {
+  const int tid = threadIdx.x;
+  if (n <= 320) {
+    for (int j = tid; j < n; j += kThreads) {
+      const unsigned long long key = sm.list[j];
+      int rank = 0;
+      for (int i = 0; i < n; ++i) rank += (sm.list[i] < key) ? 1 : 0;
+      sm.sorted[rank] = key;
+    }
+    __syncthreads();
+    return;
+  }
+  int np = 512;
+  while (np < n) np <<= 1;
+  for (int j = tid; j < np; j += kThreads) sm.sorted[j] = j < n ? sm.list[j] : ~0ull;
+  __syncthreads();
+  for (int k = 2; k <= np; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = tid; t < (np >> 1); t += kThreads) {
+        const int i = ((t & ~(j - 1)) << 1) | (t & (j - 1));  // lower element of the pair
+        const int l = i | j;
+        const unsigned long long a = sm.sorted[i], b = sm.sorted[l];
+        const bool up = (i & k) == 0;
+        if ((a > b) == up) { sm.sorted[i] = b; sm.sorted[l] = a; }
+      }
+      __syncthreads();
+    }
+  }
 }
 
 struct SoftFwdOut {
@@ -575,18 +635,8 @@ __device__ __forceinline__ void soft_tile(const Scene& s, const TileCtx& c, Tile
   bool first_window = true;
   int lo = -1;
   while (true) {
-    int hi = 0x7fffffff;
-    int n = soft_collect<false>(s, c, sm, lo, hi);
-    if (n > kSoftCap) {
-      // pathological density: take the largest window (lo, hi] holding <= kSoftCap candidates
-      int L = lo + 1, R = maxf - 1;
-      while (L < R) {
-        const int mid = L + (R - L + 1) / 2;
-        if (soft_collect<true>(s, c, sm, lo, mid) <= kSoftCap) L = mid; else R = mid - 1;
-      }
-      hi = L;
-      n = soft_collect<false>(s, c, sm, lo, hi);
-    }
+    int hi;
+    int n = soft_window(s, c, sm, lo, maxf, hi);
     if (!BWD && cache && first_window) {
       first_window = false;
       if (tid == 0) {
@@ -604,14 +654,7 @@ __device__ __forceinline__ void soft_tile(const Scene& s, const TileCtx& c, Tile
       __syncthreads();
       if (sm.pool_slot >= 0) blk = s.pool_data + (size_t)sm.pool_slot * 3 * E;
     }
-    // rank sort by face index (keys are unique: a face lives in one level, a tile reads one bin per level)
-    for (int j = tid; j < n; j += kThreads) {
-      const unsigned long long key = sm.list[j];
-      int rank = 0;
-      for (int i = 0; i < n; ++i) rank += (sm.list[i] < key) ? 1 : 0;
-      sm.sorted[rank] = key;
-    }
-    __syncthreads();
+    soft_sort(sm, n);  // by face index
     bool all_done = false;
     for (int c0 = 0; c0 < n && !all_done; c0 += kChunk) {
       const int cn = min(kChunk, n - c0);
@@ -765,18 +808,8 @@ __device__ __forceinline__ void soft_tile_fwd(const Scene& s, const TileCtx& c, 
   bool first_window = true;
   int lo = -1;
   while (true) {
-    int hi = 0x7fffffff;
-    int n = soft_collect<false>(s, c, sm, lo, hi);
-    if (n > kSoftCap) {
-      // pathological density: take the largest window (lo, hi] holding <= kSoftCap candidates
-      int L = lo + 1, R = maxf - 1;
-      while (L < R) {
-        const int mid = L + (R - L + 1) / 2;
-        if (soft_collect<true>(s, c, sm, lo, mid) <= kSoftCap) L = mid; else R = mid - 1;
-      }
-      hi = L;
-      n = soft_collect<false>(s, c, sm, lo, hi);
-    }
+    int hi;
+    int n = soft_window(s, c, sm, lo, maxf, hi);
     if (first_window) {
       first_window = false;
       if (tid == 0) {
@@ -794,14 +827,7 @@ __device__ __forceinline__ void soft_tile_fwd(const Scene& s, const TileCtx& c, 
       __syncthreads();
       if (sm.pool_slot >= 0) blk = s.pool_data + (size_t)sm.pool_slot * 3 * E;
     }
-    // rank sort by face index (keys are unique: a face lives in one level, a tile reads one bin per level)
-    for (int j = tid; j < n; j += kThreads) {
-      const unsigned long long key = sm.list[j];
-      int rank = 0;
-      for (int i = 0; i < n; ++i) rank += (sm.list[i] < key) ? 1 : 0;
-      sm.sorted[rank] = key;
-    }
-    __syncthreads();
+    soft_sort(sm, n);  // by face index
     bool all_done = false;
     for (int c0 = 0; c0 < n && !all_done; c0 += kChunk) {
       const int cn = min(kChunk, n - c0);
@@ -1108,18 +1134,9 @@ __global__ void __launch_bounds__(kThreads) soft_enum_kernel(const __grid_consta
     bool first_window = true, cached = true;
     int lo = -1;
     while (true) {
-      int hi = 0x7fffffff;
-      int n = soft_collect<false>(s, c, sm, lo, hi);
+      int hi;
+      int n = soft_window(s, c, sm, lo, maxf, hi);
       if (first_window && active) { const int p = sm.apix[tid]; lx = p & 15; ly = p >> 4; }
-      if (n > kSoftCap) {
-        int L = lo + 1, R = maxf - 1;
-        while (L < R) {
-          const int mid = L + (R - L + 1) / 2;
-          if (soft_collect<true>(s, c, sm, lo, mid) <= kSoftCap) L = mid; else R = mid - 1;
-        }
-        hi = L;
-        n = soft_collect<false>(s, c, sm, lo, hi);
-      }
       const bool alloc = first_window;
       if (first_window) {
         first_window = false;
@@ -1135,13 +1152,7 @@ __global__ void __launch_bounds__(kThreads) soft_enum_kernel(const __grid_consta
           sm.nent = 0;
         }
       }
-      for (int j = tid; j < n; j += kThreads) {
-        const unsigned long long key = sm.list[j];
-        int rank = 0;
-        for (int i = 0; i < n; ++i) rank += (sm.list[i] < key) ? 1 : 0;
-        sm.sorted[rank] = key;
-      }
-      __syncthreads();
+      soft_sort(sm, n);  // by face index
       if (alloc) {
         if (sm.pool_slot < 0) { cached = false; break; }  // uniform: handed over to the single-kernel path
         blk = s.pool_data + (size_t)sm.pool_slot * 3 * E;

@@ -110,6 +110,43 @@ def test_fused_dibr_vs_reference_cuda(name):
     assert rel_err(g_ff, N(r["grad_ff"])) <= 3e-5
 
 
+CONFIG_CASES = {
+    # BASELINE.json configs at (or cut down from) their full sizes, against the reference's own
+    # CUDA kernels on the same GPU.  (name: views, icosphere level, H, W)
+    "c2_full_8x5120f_256": (8, 4, 256, 256),            # configs[1] exactly
+    "c3_cut_4x20480f_512": (4, 5, 512, 512),            # configs[2], 4 of 64 views
+    "c4_cut_2x20480f_1024": (2, 5, 1024, 1024),         # configs[3], 2 of 256 views (fp32 features)
+    "c5_cut_1x1310720f_2048": (1, 8, 2048, 2048),       # configs[4], 1 of 8 views, 1.3 M triangles
+}
+
+
+@pytest.mark.skipif(not ref_cuda.available(), reason="oracle/_ref (reference CUDA build) not present")
+@pytest.mark.parametrize("name", list(CONFIG_CASES))
+def test_baseline_configs_vs_reference_cuda(name):
+    B, level, H, W = CONFIG_CASES[name]
+    fvz, fvi, fnz = synthetic.icosphere_views(B, level, seed=1234, same_mesh=(level >= 8))
+    F = fvz.shape[1]
+    ff = synthetic.random_features(B, F, 3, seed=99)
+    gen = torch.Generator(device=DEV); gen.manual_seed(7)
+    g_feat = torch.rand((B, H, W, 3), device=DEV, generator=gen)
+    g_soft = torch.rand((B, H, W), device=DEV, generator=gen)
+    t_fvz, t_fnz = T(fvz), T(fnz)
+    t_fvi, t_ff = T(fvi, True), T(ff, True)
+    feat, soft, idx = dibr_rasterization(H, W, t_fvz, t_fvi, t_ff, t_fnz)
+    torch.autograd.backward([feat, soft], [g_feat, g_soft])
+    r = ref_cuda.dibr_forward_backward(H, W, t_fvz, t_fvi.detach(), t_ff.detach(), t_fnz, g_feat, g_soft)
+    assert torch.equal(idx, r["face_idx"])                                   # bit-exact
+    assert 0.2 < (idx >= 0).float().mean().item() < 0.9
+    assert (feat - r["features"]).abs().max().item() <= 1e-5
+    assert (soft - r["soft_mask"]).abs().max().item() <= 1e-5
+    bit_equal = (soft == r["soft_mask"]).float().mean().item()
+    e_xy = rel_err(N(t_fvi.grad), N(r["grad_fvi"]))
+    e_ff = rel_err(N(t_ff.grad), N(r["grad_ff"]))
+    print(f"\n[{name}] face_idx exact; soft_mask bit-equal {bit_equal:.6f}; grad rel err fvi {e_xy:.2e} ff {e_ff:.2e}")
+    assert bit_equal > 0.9999
+    assert e_xy <= 3e-5 and e_ff <= 3e-5
+
+
 def test_composition_equals_separate_calls():
     """test_dibr.py:482-529: dibr_rasterization == rasterize + dibr_soft_mask, torch.equal."""
     fvz, fvi, fnz = synthetic.icosphere_views(3, 3, seed=7)
@@ -364,6 +401,25 @@ def test_soft_backward_cache_and_recompute_paths_agree(cache_tiles, monkeypatch)
     s2.backward(T(g_soft))
     o_gs = oracle.dibr_soft_mask_backward(g_soft, fvi, o_idx)
     assert rel_err(N(t_fvi.grad), o_gs) <= GRAD_REL
+
+
+def test_soft_mask_windowed_path_many_tiles():
+    """Sub-pixel triangles, > 1024 enlarged faces over every silhouette tile (the regime of
+    BASELINE configs[4]): the index-windowed walk runs in many CTAs at once."""
+    fvz, fvi, fnz = synthetic.icosphere_views(2, 6, seed=5, same_mesh=True)      # 81 920 faces
+    B, F = fvz.shape[:2]
+    H = W = 256
+    ff = synthetic.random_features(B, F, 2, seed=1)
+    t_fvi = T(fvi, True)
+    feat, soft, idx = dibr_rasterization(H, W, T(fvz), t_fvi, T(ff), T(fnz), boxlen=0.05)
+    o_feat, o_soft, o_idx = oracle.dibr_rasterization(H, W, fvz, fvi, ff, fnz, boxlen=0.05)
+    assert np.array_equal(N(idx), o_idx)
+    np.testing.assert_allclose(N(soft), o_soft, rtol=0, atol=1e-5)
+    rng = np.random.default_rng(2)
+    g_soft = rng.uniform(size=(B, H, W)).astype(np.float32)
+    soft.backward(T(g_soft))
+    o_g = oracle.dibr_soft_mask_backward(g_soft, fvi, o_idx, 7000, 0.05, 30, 1000.)
+    assert rel_err(N(t_fvi.grad), o_g) <= GRAD_REL
 
 
 def test_errors_like_reference():
