@@ -29,12 +29,17 @@ if ROOT not in sys.path:
 METRIC = "DIB-R fwd+bwd Mpixels/sec at 1024^2 per GPU; achieved HBM GB/s vs peak"
 UNIT = "Mpixels/s"
 WORKLOADS = {
-    # name: (views per GPU, icosphere level, H, W, D)
-    "c4_shard": (32, 5, 1024, 1024, 3),
-    "c2": (8, 4, 256, 256, 3),
-    "c3": (64, 5, 512, 512, 3),
-    "c5": (8, 8, 2048, 2048, 3),        # configs[4]: one 1.3 M-triangle mesh, 8 views
-    "tiny": (2, 3, 128, 128, 3),
+    # name: (views per GPU, icosphere level, H, W, D, radial vertex jitter)
+    "c4_shard": (32, 5, 1024, 1024, 3, 0.05),
+    "c2": (8, 4, 256, 256, 3, 0.05),
+    "c3": (64, 5, 512, 512, 3, 0.05),
+    # configs[4]: one 1.3 M-triangle mesh, 8 views.  "c5" scales the jitter with the edge
+    # length (a bumpy surface, ~3 px^2 triangles); "c5_spiky" keeps the level-5 jitter,
+    # 8x the edge length: sliver triangles with 20-px boxes, >2000 soft-mask candidates per
+    # tile (the index-windowed path) - a stress case, not a mesh anyone renders.
+    "c5": (8, 8, 2048, 2048, 3, 0.05 / 8),
+    "c5_spiky": (8, 8, 2048, 2048, 3, 0.05),
+    "tiny": (2, 3, 128, 128, 3, 0.05),
 }
 SIGMAINV, BOXLEN, KNUM, MULT, EPS = 7000.0, 0.02, 30, 1000.0, 1e-8
 
@@ -120,8 +125,9 @@ class ClockSampler:
 
 def make_scene(workload, rank):
     from kaolin_b200 import synthetic
-    B, level, H, W, D = WORKLOADS[workload]
-    fvz, fvi, fnz = synthetic.icosphere_views(B, level, seed=1234 + 17 * rank, same_mesh=(level >= 8))
+    B, level, H, W, D, jitter = WORKLOADS[workload]
+    fvz, fvi, fnz = synthetic.icosphere_views(B, level, seed=1234 + 17 * rank, jitter=jitter,
+                                              same_mesh=(level >= 8))
     ff = synthetic.random_features(B, fvz.shape[1], D, seed=99 + rank)
     return B, fvz.shape[1], H, W, D, fvz, fvi, fnz, ff
 
@@ -176,13 +182,14 @@ def run_reference(args):
         s.run()
     dt = (time.perf_counter() - t) / max(1, args.steps)
     val = s.pixels / dt / 1e6
-    B, level, H, W, D = WORKLOADS[args.workload]
+    B, level, H, W, D, _ = WORKLOADS[args.workload]
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
         "data": "synthetic",
-        "config": {"workload": args.workload, "views_per_gpu": B, "faces_per_view": 20 * 4 ** level,
+        "config": {"workload": args.workload, "vertex_jitter": WORKLOADS[args.workload][5],
+                   "views_per_gpu": B, "faces_per_view": 20 * 4 ** level,
                    "height": H, "width": W, "feat_dim": D, "knum": KNUM, "sample": desc},
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -395,7 +402,8 @@ def run_ours(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.workload, "views_per_gpu": B, "faces_per_view": F, "height": H,
+        "config": {"workload": args.workload, "vertex_jitter": WORKLOADS[args.workload][5],
+                   "views_per_gpu": B, "faces_per_view": F, "height": H,
                    "width": W, "feat_dim": D, "features": "fp32", "knum": KNUM, "sigmainv": SIGMAINV,
                    "boxlen": BOXLEN, "covered_fraction": covered,
                    "parallelism": f"views sharded x{world}, NCCL all-gather of per-view grads"

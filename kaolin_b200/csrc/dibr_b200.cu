@@ -78,7 +78,7 @@ struct Scene {
   uint16_t* pool_slots;   // [pool_tiles][256][32] its hit slots, face order      } 3-kernel forward
   int* fb_ctr;            // [1] tiles whose hits did not fit the cache (recomputed in backward)
   int* fb_list;           // [B*nty*ntx] their linear tile ids
-  int* tile_cnt;          // [B*nty*ntx] enlarged face rectangles over each 16x16 tile (count pass)
+  int* tile_cnt;          // [B*nty*ceil(ntx/32)] bit per 16x16 tile: an enlarged face rectangle overlaps it (count pass)
   int* view_flag;         // [B] the view has an enlarged rectangle too big to count per tile
   int* band_ctr;          // [1] tiles with uncovered pixels under some enlarged face rectangle
   int* band_list;         // [B*nty*ntx][kBandRec] work list of the soft-mask kernels: per tile
@@ -161,72 +161,171 @@ __device__ __forceinline__ void load_xy(const Scene& s, int64_t g, float v[6]) {
 // ---------------------------------------------------------------------------
 // Binning: one thread per face; pass 1 counts, pass 2 fills (unordered inside a
 // bin; consumers that need index order sort their culled candidates).
-template <bool FILL>
-__device__ __forceinline__ void emit_rect(const Scene& s, int set, int b, int64_t fbase, int f,
-                                          const PixRect& r) {
-  if (r.x_hi <= r.x_lo || r.y_hi <= r.y_lo) return;
-  int l = 0, bx0, bx1, by0, by1;
-  for (;; ++l) {
-    const int sh = 4 + 2 * l;
-    bx0 = r.x_lo >> sh; bx1 = (r.x_hi - 1) >> sh;
-    by0 = r.y_lo >> sh; by1 = (r.y_hi - 1) >> sh;
-    if ((bx1 - bx0 <= 1 && by1 - by0 <= 1) || l == s.L - 1) break;
-  }
-  const int4 e = make_int4(f, r.x_lo | (r.x_hi << 16), r.y_lo | (r.y_hi << 16), 0);
-  for (int by = by0; by <= by1; ++by)
-    for (int bx = bx0; bx <= bx1; ++bx) {
-      const int bin = s.bin_base[l] + by * s.ntx[l] + bx;
-      const size_t ci = ((size_t)set * s.B + b) * s.NB + bin;
-      const int pos = atomicAdd(s.cnt + ci, 1);
-      if (FILL) s.entries[(size_t)set * 4 * s.NF + 4 * fbase + s.off[ci] + pos] = e;
+// Faces that are neighbours in the index buffer are neighbours on screen, so at any
+// moment the whole GPU increments the same few bin counters, and same-address L2
+// atomics serialise at the full read-modify-write latency (measured: ~10 us per
+// returning atomic with 1.3 M faces).  The counters are therefore aggregated twice
+// before they reach L2: lanes of a warp that hit the same bin are found with
+// match.any, and the warp leaders merge into a per-CTA shared-memory hash table;
+// one global atomic per (CTA, distinct bin) is issued by a separate thread each, so
+// their round trips overlap.  The entries of a patch land contiguously.
+constexpr int kBinThreads = 512;
+constexpr int kBinHT = 4096;            // >= kBinThreads * 8 targets: the table always fits
+constexpr uint32_t kBinEmpty = 0xffffffffu;
+
+struct BinSmem {
+  uint32_t keys[kBinHT];   // counter index (set, view, bin)
+  int vals[kBinHT];        // faces of this CTA in the bin; after the flush: where they go
+};
+
+struct BinSpan { int l, bx0, bx1, by0, by1; bool has; };
+
+__device__ __forceinline__ BinSpan bin_span(const Scene& s, const PixRect& r, bool has) {
+  BinSpan sp;
+  sp.has = has && r.x_hi > r.x_lo && r.y_hi > r.y_lo;
+  sp.l = 0; sp.bx0 = 0; sp.bx1 = -1; sp.by0 = 0; sp.by1 = -1;
+  if (sp.has) {
+    for (;; ++sp.l) {
+      const int sh = 4 + 2 * sp.l;
+      sp.bx0 = r.x_lo >> sh; sp.bx1 = (r.x_hi - 1) >> sh;
+      sp.by0 = r.y_lo >> sh; sp.by1 = (r.y_hi - 1) >> sh;
+      if ((sp.bx1 - sp.bx0 <= 1 && sp.by1 - sp.by0 <= 1) || sp.l == s.L - 1) break;
     }
+  }
+  return sp;
+}
+
+// Registers the <= 2x2 bins of one face in the CTA table; where[k] = (table slot << 16) | rank
+// inside the CTA, or -1.  Called by all lanes of the warp.
+__device__ __forceinline__ void bin_insert(const Scene& s, BinSmem& sm, int set, int b, const BinSpan& sp,
+                                           int (&where)[4]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const int bx = sp.bx0 + (k & 1), by = sp.by0 + (k >> 1);
+    const bool on = sp.has && bx <= sp.bx1 && by <= sp.by1;
+    const unsigned act = __ballot_sync(kFull, on);
+    where[k] = -1;
+    if (!on) continue;
+    const uint32_t ci = (uint32_t)((set * s.B + b) * s.NB + s.bin_base[sp.l] + by * s.ntx[sp.l] + bx);
+    const unsigned peers = __match_any_sync(act, ci);
+    const int leader = __ffs(peers) - 1;
+    int w = 0;
+    if (lane == leader) {
+      uint32_t h = (ci * 2654435761u) >> 20;
+      while (true) {
+        const uint32_t prev = atomicCAS(&sm.keys[h], kBinEmpty, ci);
+        if (prev == kBinEmpty || prev == ci) break;
+        h = (h + 1) & (kBinHT - 1);
+      }
+      w = (int)(h << 16) | atomicAdd(&sm.vals[h], __popc(peers));
+    }
+    w = __shfl_sync(peers, w, leader);
+    where[k] = w + __popc(peers & ((1u << lane) - 1u));
+  }
 }
 
 template <bool FILL>
-__global__ void __launch_bounds__(256) bin_faces_kernel(Scene s, int sets) {
-  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= s.NF) return;
+__global__ void __launch_bounds__(kBinThreads) bin_faces_kernel(Scene s, int sets) {
+  __shared__ BinSmem sm;
+  const int tid = threadIdx.x;
+  for (int t = tid; t < kBinHT; t += kBinThreads) { sm.keys[t] = kBinEmpty; sm.vals[t] = 0; }
+  __syncthreads();
+  int64_t i = (int64_t)blockIdx.x * kBinThreads + tid;
+  const bool live = i < s.NF;
+  if (!live) i = s.NF - 1;
   int b; int64_t fbase;
   face_view(s, i, b, fbase);
   const int f = (int)(i - fbase);
   float v[6];
   load_xy(s, i, v);
-  bool valid = true;
-  if (s.fnz) valid = __ldg(s.fnz + i) >= 0.f;
+  bool valid = live;
+  if (s.fnz) valid = valid && __ldg(s.fnz + i) >= 0.f;
   if (s.valid) valid = valid && (__ldg(s.valid + i) != 0);
-  float xmin, ymin, xmax, ymax;
-  if ((sets & 1) && valid) {
-    if (s.bbox_tight) {
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(s.bbox_tight) + i);
+  PixRect r[2];
+  BinSpan sp[2];
+  int where[2][4];
+#pragma unroll
+  for (int set = 0; set < 2; ++set) {
+    sp[set].has = false;
+    if (!((sets >> set) & 1)) continue;
+    float xmin, ymin, xmax, ymax;
+    const float* given = set ? s.bbox_large : s.bbox_tight;
+    if (given) {
+      const float4 bb = __ldg(reinterpret_cast<const float4*>(given) + i);
       xmin = bb.x; ymin = bb.y; xmax = bb.z; ymax = bb.w;
-    } else {  // torch.min / torch.max over the 3 vertices (rasterization.py:325-327)
+    } else {
+      // tight: torch.min / torch.max over the 3 vertices (rasterization.py:325-327);
+      // large: [min - boxlen*m, max + boxlen*m] in fp32 (dibr.py:33-39)
       xmin = fminf(fminf(v[0], v[2]), v[4]); ymin = fminf(fminf(v[1], v[3]), v[5]);
       xmax = fmaxf(fmaxf(v[0], v[2]), v[4]); ymax = fmaxf(fmaxf(v[1], v[3]), v[5]);
+      if (set) { xmin = fsub(xmin, s.margin); ymin = fsub(ymin, s.margin); xmax = fadd(xmax, s.margin); ymax = fadd(ymax, s.margin); }
     }
-    emit_rect<FILL>(s, 0, b, fbase, f, bbox_to_rect(s.grid, xmin, ymin, xmax, ymax));
-  }
-  if (sets & 2) {
-    if (s.bbox_large) {
-      const float4 bb = __ldg(reinterpret_cast<const float4*>(s.bbox_large) + i);
-      xmin = bb.x; ymin = bb.y; xmax = bb.z; ymax = bb.w;
-    } else {  // dibr.py:33-39: [min - boxlen*m, max + boxlen*m], fp32
-      xmin = fsub(fminf(fminf(v[0], v[2]), v[4]), s.margin);
-      ymin = fsub(fminf(fminf(v[1], v[3]), v[5]), s.margin);
-      xmax = fadd(fmaxf(fmaxf(v[0], v[2]), v[4]), s.margin);
-      ymax = fadd(fmaxf(fmaxf(v[1], v[3]), v[5]), s.margin);
-    }
-    const PixRect r = bbox_to_rect(s.grid, xmin, ymin, xmax, ymax);
-    emit_rect<FILL>(s, 1, b, fbase, f, r);
-    if (!FILL && r.x_hi > r.x_lo && r.y_hi > r.y_lo) {
-      // which 16x16 tiles can see this face in the soft mask (filters the soft-mask work list)
-      const int tx0 = r.x_lo >> 4, tx1 = (r.x_hi - 1) >> 4, ty0 = r.y_lo >> 4, ty1 = (r.y_hi - 1) >> 4;
-      if ((tx1 - tx0 + 1) * (ty1 - ty0 + 1) <= 64) {
-        for (int ty = ty0; ty <= ty1; ++ty)
-          for (int tx = tx0; tx <= tx1; ++tx)
-            atomicAdd(s.tile_cnt + ((size_t)b * s.nty[0] + ty) * s.ntx[0] + tx, 1);
-      } else {
-        atomicOr(s.view_flag + b, 1);
+    r[set] = bbox_to_rect(s.grid, xmin, ymin, xmax, ymax);
+    sp[set] = bin_span(s, r[set], set ? live : valid);
+    const bool small = sp[set].bx1 - sp[set].bx0 <= 1 && sp[set].by1 - sp[set].by0 <= 1;
+    if (__all_sync(kFull, small)) {
+      bin_insert(s, sm, set, b, sp[set], where[set]);
+    } else {
+      // a warp with a face of the coarsest level spanning more than 2x2 bins: plain atomics
+#pragma unroll
+      for (int k = 0; k < 4; ++k) where[set][k] = -1;
+      if (sp[set].has) {
+        const int4 e = make_int4(f, r[set].x_lo | (r[set].x_hi << 16), r[set].y_lo | (r[set].y_hi << 16), 0);
+        for (int by = sp[set].by0; by <= sp[set].by1; ++by)
+          for (int bx = sp[set].bx0; bx <= sp[set].bx1; ++bx) {
+            const size_t ci = ((size_t)set * s.B + b) * s.NB + s.bin_base[sp[set].l] + by * s.ntx[sp[set].l] + bx;
+            const int pos = atomicAdd(s.cnt + ci, 1);
+            if (FILL) s.entries[(size_t)set * 4 * s.NF + 4 * fbase + s.off[ci] + pos] = e;
+          }
       }
+    }
+  }
+  if (!FILL && (sets & 2) && live && r[1].x_hi > r[1].x_lo && r[1].y_hi > r[1].y_lo) {
+    // which 16x16 tiles can see this face in the soft mask (filters the soft-mask work
+    // list): one bit per tile, a row of tiles per 32-bit word, so a face ORs one word per
+    // tile row
+    const int tx0 = r[1].x_lo >> 4, tx1 = (r[1].x_hi - 1) >> 4, ty0 = r[1].y_lo >> 4, ty1 = (r[1].y_hi - 1) >> 4;
+    const int w0 = tx0 >> 5, w1 = tx1 >> 5, nw = (s.ntx[0] + 31) >> 5;
+    if ((ty1 - ty0 + 1) * (w1 - w0 + 1) <= 64) {
+      for (int w = w0; w <= w1; ++w) {
+        const int lo = max(tx0 - (w << 5), 0), hi = min(tx1 - (w << 5), 31);
+        const uint32_t m = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
+        // a (possibly stale) L1 copy that already shows the bits saves the reduction: the
+        // faces of a patch all set the same words, and same-address reductions serialise
+        for (int t0 = ty0; t0 <= ty1; t0 += 8) {
+          int* p = s.tile_cnt + ((size_t)b * s.nty[0] + t0) * nw + w;
+          uint32_t have[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) have[j] = t0 + j <= ty1 ? (uint32_t)__ldca(p + (size_t)j * nw) : m;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if ((have[j] & m) != m) atomicOr(p + (size_t)j * nw, (int)m);
+        }
+      }
+    } else {
+      atomicOr(s.view_flag + b, 1);
+    }
+  }
+  __syncthreads();
+  // one global atomic per distinct bin of this CTA, each from its own thread
+  for (int t = tid; t < kBinHT; t += kBinThreads) {
+    const uint32_t ci = sm.keys[t];
+    if (ci != kBinEmpty) {
+      const int pos = atomicAdd(s.cnt + ci, sm.vals[t]);
+      if (FILL) sm.vals[t] = pos + s.off[ci];
+    }
+  }
+  if (!FILL) return;
+  __syncthreads();
+#pragma unroll
+  for (int set = 0; set < 2; ++set) {
+    const int4 e = make_int4(f, r[set].x_lo | (r[set].x_hi << 16), r[set].y_lo | (r[set].y_hi << 16), 0);
+    int4* dst = s.entries + (size_t)set * 4 * s.NF + 4 * fbase;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int w = where[set][k];
+      if (sp[set].has && w >= 0) dst[sm.vals[w >> 16] + (w & 0xffff)] = e;
     }
   }
 }
@@ -1038,7 +1137,8 @@ __global__ void __launch_bounds__(kThreads, 6) dibr_tile_fwd_kernel(const __grid
       if (wv) atomicOr(&sm.any_uncovered, 1);
       __threadfence_block();
       if (atomicAdd(&sm.warps_done, 1) == kThreads / 32 - 1 && atomicOr(&sm.any_uncovered, 0)) {
-        const int nlarge = __ldg(s.tile_cnt + tile_linear(s, c)) + __ldg(s.view_flag + c.b);
+        const int nlarge = ((__ldg(s.tile_cnt + ((size_t)c.b * s.nty[0] + c.ty) * ((s.ntx[0] + 31) >> 5) + (c.tx >> 5)) >> (c.tx & 31)) & 1) +
+                           __ldg(s.view_flag + c.b);
         if (nlarge > 0) {
           // work-list record: everything the soft-mask kernels need to start without
           // re-reading face_idx or the bin tables
@@ -1575,6 +1675,7 @@ int setup_scene(Scene& s, int B, int64_t NF, int F, int H, int W, float multipli
     nb += s.ntx[l] * s.nty[l];
   }
   s.NB = nb;
+  if ((int64_t)2 * B * nb >= 0x7fffffffLL) return DIBR_B200_ESIZE;  // counter ids are 32-bit
   s.cnt = (int*)p;
   s.pool_ctr = s.cnt + (size_t)2 * B * nb;
   s.fb_ctr = s.pool_ctr + 1;
@@ -1622,10 +1723,10 @@ int build_bins(const Scene& s, int sets, cudaStream_t st) {
   cudaError_t e = cudaMemsetAsync(s.cnt, 0, zero_ints * sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
   if (s.NF > 0) {
-    const unsigned blocks = (unsigned)((s.NF + 255) / 256);
-    bin_faces_kernel<false><<<blocks, 256, 0, st>>>(s, sets);
+    const unsigned blocks = (unsigned)((s.NF + kBinThreads - 1) / kBinThreads);
+    bin_faces_kernel<false><<<blocks, kBinThreads, 0, st>>>(s, sets);
     scan_bins_kernel<<<2 * s.B, 1024, 0, st>>>(s);
-    bin_faces_kernel<true><<<blocks, 256, 0, st>>>(s, sets);
+    bin_faces_kernel<true><<<blocks, kBinThreads, 0, st>>>(s, sets);
   }
   return (int)cudaGetLastError();
 }

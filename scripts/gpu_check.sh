@@ -34,6 +34,6 @@ PY
     full:*)
       rx=${what#full:}
       cp kaolin_b200/csrc/libdibr_b200.so gpurun_out/lib_$tag.so
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$rx" -s ${NCU_SKIP:-3} -c ${NCU_COUNT:-4} -o gpurun_out/prof_$tag -f python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-ref-cuda > gpurun_out/ncu_full_$tag.log 2>&1; echo "ncu full exit $?" ;;
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:"$rx" -s ${NCU_SKIP:-3} -c ${NCU_COUNT:-4} -o gpurun_out/prof_$tag -f python bench.py ${BENCH_ARGS:-} --steps 2 --warmup 1 --no-cpu-baseline --no-ref-cuda > gpurun_out/ncu_full_$tag.log 2>&1; echo "ncu full exit $?" ;;
   esac
 done

@@ -112,19 +112,21 @@ def test_fused_dibr_vs_reference_cuda(name):
 
 CONFIG_CASES = {
     # BASELINE.json configs at (or cut down from) their full sizes, against the reference's own
-    # CUDA kernels on the same GPU.  (name: views, icosphere level, H, W)
-    "c2_full_8x5120f_256": (8, 4, 256, 256),            # configs[1] exactly
-    "c3_cut_4x20480f_512": (4, 5, 512, 512),            # configs[2], 4 of 64 views
-    "c4_cut_2x20480f_1024": (2, 5, 1024, 1024),         # configs[3], 2 of 256 views (fp32 features)
-    "c5_cut_1x1310720f_2048": (1, 8, 2048, 2048),       # configs[4], 1 of 8 views, 1.3 M triangles
+    # CUDA kernels on the same GPU.  (name: views, icosphere level, H, W, vertex jitter)
+    "c2_full_8x5120f_256": (8, 4, 256, 256, 0.05),            # configs[1] exactly
+    "c3_cut_4x20480f_512": (4, 5, 512, 512, 0.05),            # configs[2], 4 of 64 views
+    "c4_cut_2x20480f_1024": (2, 5, 1024, 1024, 0.05),         # configs[3], 2 of 256 views (fp32 features)
+    "c5_cut_1x1310720f_2048": (1, 8, 2048, 2048, 0.05 / 8),   # configs[4], 1 of 8 views, 1.3 M triangles
+    # same mesh with the jitter 8x the edge length: slivers, >2000 soft-mask candidates per tile
+    "c5_spiky_1x1310720f_2048": (1, 8, 2048, 2048, 0.05),
 }
 
 
 @pytest.mark.skipif(not ref_cuda.available(), reason="oracle/_ref (reference CUDA build) not present")
 @pytest.mark.parametrize("name", list(CONFIG_CASES))
 def test_baseline_configs_vs_reference_cuda(name):
-    B, level, H, W = CONFIG_CASES[name]
-    fvz, fvi, fnz = synthetic.icosphere_views(B, level, seed=1234, same_mesh=(level >= 8))
+    B, level, H, W, jitter = CONFIG_CASES[name]
+    fvz, fvi, fnz = synthetic.icosphere_views(B, level, seed=1234, jitter=jitter, same_mesh=(level >= 8))
     F = fvz.shape[1]
     ff = synthetic.random_features(B, F, 3, seed=99)
     gen = torch.Generator(device=DEV); gen.manual_seed(7)
