@@ -56,6 +56,10 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-ref-cuda", action="store_true")
     p.add_argument("--ref-cuda-views", type=int, default=2)
+    p.add_argument("--chunks", type=int, default=1,
+                   help="N > 1: 1 = the all-gather of grad_face_features overlaps the soft-mask branch of "
+                        "the backward (default); k > 1 = k view-chunks per step, chunk i's all-gather "
+                        "overlaps chunk i+1 (measured slower at 32 views per GPU: smaller launches)")
     return p.parse_args()
 
 
@@ -204,7 +208,7 @@ def run_ours(args):
     import torch.distributed as dist
     from kaolin_b200 import _lib
     from kaolin_b200.render.mesh import _host, dibr_rasterization
-    from kaolin_b200.multi_gpu import all_gather_view_grads
+    from kaolin_b200.multi_gpu import ChunkedGradAllGather, OverlappedGradAllGather, chunk_ranges
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -233,21 +237,36 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     # ---- resident path: C ABI with device pointers (value) ----------------
+    # N > 1: the all-gather of grad_face_features (final after the rasterize branch of the
+    # backward) travels while the soft-mask branch runs; grad_face_vertices_image follows.
+    spans = chunk_ranges(B, args.chunks) if world > 1 else [(0, B)]
+
     def step_resident(ev=None):
-        if ev: ev[0].record()
-        feat, idx, wts, soft, ws = _host.forward(mode, H, W, d_fvz, d_fvi, d_ff, d_fnz, None, MULT, EPS,
-                                                 SIGMAINV, boxlen_m, KNUM)
-        if ev: ev[1].record()
-        g_fvi, g_ff = _host.backward(H, W, g_feat, g_soft, idx, wts, soft, d_fvi, d_ff, MULT, EPS,
-                                     SIGMAINV, boxlen_m, KNUM, ws, True)
-        if ev: ev[2].record()
-        if world > 1:
-            g_fvi, g_ff = all_gather_view_grads([g_fvi, g_ff], B * world)
+        chunked = ChunkedGradAllGather(B) if world > 1 and len(spans) > 1 else None
+        for ci, (c0, c1) in enumerate(spans):
+            if ev: ev[3 * ci].record()
+            feat, idx, wts, soft, ws = _host.forward(mode, H, W, d_fvz[c0:c1], d_fvi[c0:c1], d_ff[c0:c1],
+                                                     d_fnz[c0:c1], None, MULT, EPS, SIGMAINV, boxlen_m, KNUM)
+            if ev: ev[3 * ci + 1].record()
+            bwd = lambda: _host.backward(H, W, g_feat[c0:c1], g_soft[c0:c1], idx, wts, soft, d_fvi[c0:c1],
+                                         d_ff[c0:c1], MULT, EPS, SIGMAINV, boxlen_m, KNUM, ws, True)
+            if world > 1 and chunked is None:
+                with OverlappedGradAllGather(B * world) as gather:
+                    g_fvi, g_ff = bwd()
+                if ev: ev[3 * ci + 2].record()
+                g_fvi, g_ff = gather.finish(g_fvi)
+            else:
+                g_fvi, g_ff = bwd()
+                if ev: ev[3 * ci + 2].record()
+                if chunked is not None:
+                    chunked.submit(c0, c1, [g_fvi, g_ff])
+        if chunked is not None:
+            g_fvi, g_ff = chunked.finish()
         return g_fvi, g_ff
 
     for _ in range(args.warmup):
         step_resident()
-    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3 * len(spans))] for _ in range(args.steps)]
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
@@ -258,8 +277,9 @@ def run_ours(args):
     barrier()
     clocks = sampler.stop()
     total_ms = start.elapsed_time(end)
-    fwd_ms = statistics.mean(e[0].elapsed_time(e[1]) for e in evs)
-    bwd_ms = statistics.mean(e[1].elapsed_time(e[2]) for e in evs)
+    nch = len(spans)
+    fwd_ms = statistics.mean(sum(e[3 * c].elapsed_time(e[3 * c + 1]) for c in range(nch)) for e in evs)
+    bwd_ms = statistics.mean(sum(e[3 * c + 1].elapsed_time(e[3 * c + 2]) for c in range(nch)) for e in evs)
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -314,14 +334,33 @@ def run_ours(args):
                 a_ff.copy_(h_ff, non_blocking=True); a_fnz.copy_(h_fnz, non_blocking=True)
             ev_up = torch.cuda.Event(); ev_up.record(s_h2d)
         s_cmp.wait_event(ev_up)
-        a_fvi.grad = None; a_ff.grad = None
-        feat, soft, idx = dibr_rasterization(H, W, a_fvz, a_fvi, a_ff, a_fnz, SIGMAINV, BOXLEN, KNUM)
-        torch.autograd.backward([feat, soft], [g_feat, g_soft])
-        g1, g2 = a_fvi.grad, a_ff.grad
-        if world > 1:
-            full = all_gather_view_grads([g1, g2], B * world)
+        if world == 1:
+            a_fvi.grad = None; a_ff.grad = None
+            feat, soft, idx = dibr_rasterization(H, W, a_fvz, a_fvi, a_ff, a_fnz, SIGMAINV, BOXLEN, KNUM)
+            torch.autograd.backward([feat, soft], [g_feat, g_soft])
+            g1, g2 = a_fvi.grad, a_ff.grad
+            loss = (soft.detach().sum() / soft.numel()).reshape(1)
+        elif len(spans) == 1:
+            a_fvi.grad = None; a_ff.grad = None
+            feat, soft, idx = dibr_rasterization(H, W, a_fvz, a_fvi, a_ff, a_fnz, SIGMAINV, BOXLEN, KNUM)
+            with OverlappedGradAllGather(B * world) as gather:
+                torch.autograd.backward([feat, soft], [g_feat, g_soft])
+            full = gather.finish(a_fvi.grad, a_ff.grad)
             g1, g2 = full[0][rank * B:(rank + 1) * B], full[1][rank * B:(rank + 1) * B]
-        loss = (soft.detach().sum() / soft.numel()).reshape(1)
+            loss = (soft.detach().sum() / soft.numel()).reshape(1)
+        else:
+            gather = ChunkedGradAllGather(B)
+            loss = torch.zeros(1, device=dev)
+            for c0, c1 in spans:
+                c_fvi = a_fvi[c0:c1].detach().requires_grad_(True)
+                c_ff = a_ff[c0:c1].detach().requires_grad_(True)
+                feat, soft, idx = dibr_rasterization(H, W, a_fvz[c0:c1], c_fvi, c_ff, a_fnz[c0:c1],
+                                                     SIGMAINV, BOXLEN, KNUM)
+                torch.autograd.backward([feat, soft], [g_feat[c0:c1], g_soft[c0:c1]])
+                gather.submit(c0, c1, [c_fvi.grad, c_ff.grad])
+                loss += soft.detach().sum() / (B * H * W)
+            full = gather.finish()
+            g1, g2 = full[0][rank * B:(rank + 1) * B], full[1][rank * B:(rank + 1) * B]
         ev_done = torch.cuda.Event(); ev_done.record(s_cmp)
         ev_free[slot] = ev_done
         if ev_read[slot] is not None:          # host has consumed this slot's previous result
@@ -406,7 +445,10 @@ def run_ours(args):
                    "views_per_gpu": B, "faces_per_view": F, "height": H,
                    "width": W, "feat_dim": D, "features": "fp32", "knum": KNUM, "sigmainv": SIGMAINV,
                    "boxlen": BOXLEN, "covered_fraction": covered,
-                   "parallelism": f"views sharded x{world}, NCCL all-gather of per-view grads"
+                   "parallelism": (f"views sharded x{world}; NCCL all-gather of per-view grads, "
+                                   + ("grad_face_features' gather overlapped with the soft-mask backward"
+                                      if len(spans) == 1 else
+                                      f"{len(spans)} view-chunks per step, chunk i's gather overlaps chunk i+1"))
                    if world > 1 else "single GPU",
                    "l2": "per-step working set (>1 GB of images) exceeds the 126 MB L2; no flush needed"},
         "clocks": clocks,
@@ -415,7 +457,7 @@ def run_ours(args):
                 "api": "kaolin_b200.render.mesh.dibr_rasterization + autograd, pinned host buffers; "
                        "uploads/downloads double-buffered on side streams",
                 "host_wall_ms_per_step": wall_ms / args.steps},
-        "gpu_launches": 10 * args.steps,
+        "gpu_launches": 10 * len(spans) * args.steps,   # 6 forward + 4 backward kernels per (chunk of a) step
         "roofline": roofline,
         "triangle_pixel_tests_per_s": {
             "brute_force_equivalent": float(B) * H * W * F * 0.5 / (fwd_ms * 1e-3),

@@ -39,6 +39,10 @@ extern "C" {
 #define DIBR_B200_RASTER 1     /* compute face_idx / weights / features */
 #define DIBR_B200_SOFT_MASK 2  /* compute soft_mask */
 
+/* backward `flags` bits */
+#define DIBR_B200_BINS_VALID 1  /* workspace still holds forward's bins / hit cache for the same inputs */
+#define DIBR_B200_ACCUMULATE 2  /* add into grad_face_vertices_image instead of overwriting it */
+
 typedef struct CUstream_st* dibr_b200_stream_t; /* == cudaStream_t */
 
 int dibr_b200_version(void);
@@ -91,7 +95,11 @@ int dibr_b200_forward(
  *  grad_features  (B,H,W,D) f32 or NULL (skips the rasterize branch; grad_face_features is zeroed)
  *  grad_soft_mask (B,H,W)   f32 or NULL (skips the soft-mask branch)
  *  soft_mask      forward's output (needed only with grad_soft_mask)
- *  bins_valid     1: workspace still holds forward's bins for the same inputs
+ *  flags          DIBR_B200_BINS_VALID: workspace still holds forward's bins for the same
+ *                 inputs.  DIBR_B200_ACCUMULATE: grad_face_vertices_image is added to, not
+ *                 zeroed first - lets a caller run the two branches as two calls (e.g. to
+ *                 start sending grad_face_features while the soft-mask branch still runs);
+ *                 grad_face_features is only touched when grad_features is given.
  */
 int dibr_b200_backward(
     int batch, int num_faces, int height, int width, int feat_dim,
@@ -100,7 +108,7 @@ int dibr_b200_backward(
     const float* face_vertices_image, const float* face_features,
     float multiplier, float eps, float sigmainv, float boxlen_m, int knum,
     float* grad_face_vertices_image, float* grad_face_features,
-    void* workspace, size_t workspace_bytes, int bins_valid, dibr_b200_stream_t stream);
+    void* workspace, size_t workspace_bytes, int flags, dibr_b200_stream_t stream);
 
 /*
  * Operator: kaolin::packed_rasterize_forward_cuda

@@ -20,6 +20,7 @@ NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
 
 EINVAL, EWORKSPACE, ESIZE = -1, -3, -4
 RASTER, SOFT_MASK = 1, 2
+BINS_VALID, ACCUMULATE = 1, 2      # dibr_b200_backward flags
 
 _lock = threading.Lock()
 _lib = None

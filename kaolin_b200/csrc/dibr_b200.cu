@@ -25,6 +25,7 @@
 // on the face id (rasterize branch) and a dense stream over the cached pairs
 // (soft-mask branch; tiles outside the cache are recomputed).
 #include <cuda_runtime.h>
+#include <type_traits>
 #include <stdint.h>
 
 #include "../../include/dibr_b200.h"
@@ -225,12 +226,15 @@ __device__ __forceinline__ void bin_insert(const Scene& s, BinSmem& sm, int set,
   }
 }
 
-template <bool FILL>
-__global__ void __launch_bounds__(kBinThreads) bin_faces_kernel(Scene s, int sets) {
-  __shared__ BinSmem sm;
+// AGG = false (sparse meshes, a few faces per tile): plain atomics, no table.
+template <bool FILL, bool AGG>
+__global__ void __launch_bounds__(kBinThreads, 2) bin_faces_kernel(Scene s, int sets) {
+  __shared__ typename std::conditional<AGG, BinSmem, int>::type sm;
   const int tid = threadIdx.x;
-  for (int t = tid; t < kBinHT; t += kBinThreads) { sm.keys[t] = kBinEmpty; sm.vals[t] = 0; }
-  __syncthreads();
+  if constexpr (AGG) {
+    for (int t = tid; t < kBinHT; t += kBinThreads) { sm.keys[t] = kBinEmpty; sm.vals[t] = 0; }
+    __syncthreads();
+  }
   int64_t i = (int64_t)blockIdx.x * kBinThreads + tid;
   const bool live = i < s.NF;
   if (!live) i = s.NF - 1;
@@ -264,10 +268,13 @@ __global__ void __launch_bounds__(kBinThreads) bin_faces_kernel(Scene s, int set
     r[set] = bbox_to_rect(s.grid, xmin, ymin, xmax, ymax);
     sp[set] = bin_span(s, r[set], set ? live : valid);
     const bool small = sp[set].bx1 - sp[set].bx0 <= 1 && sp[set].by1 - sp[set].by0 <= 1;
-    if (__all_sync(kFull, small)) {
-      bin_insert(s, sm, set, b, sp[set], where[set]);
-    } else {
-      // a warp with a face of the coarsest level spanning more than 2x2 bins: plain atomics
+    bool aggregated = false;
+    if constexpr (AGG) {
+      aggregated = __all_sync(kFull, small);
+      if (aggregated) bin_insert(s, sm, set, b, sp[set], where[set]);
+    }
+    if (!aggregated) {
+      // (also: a warp with a face of the coarsest level spanning more than 2x2 bins)
 #pragma unroll
       for (int k = 0; k < 4; ++k) where[set][k] = -1;
       if (sp[set].has) {
@@ -293,13 +300,13 @@ __global__ void __launch_bounds__(kBinThreads) bin_faces_kernel(Scene s, int set
         const uint32_t m = (0xffffffffu >> (31 - hi)) & (0xffffffffu << lo);
         // a (possibly stale) L1 copy that already shows the bits saves the reduction: the
         // faces of a patch all set the same words, and same-address reductions serialise
-        for (int t0 = ty0; t0 <= ty1; t0 += 8) {
+        for (int t0 = ty0; t0 <= ty1; t0 += 4) {
           int* p = s.tile_cnt + ((size_t)b * s.nty[0] + t0) * nw + w;
-          uint32_t have[8];
+          uint32_t have[4];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) have[j] = t0 + j <= ty1 ? (uint32_t)__ldca(p + (size_t)j * nw) : m;
+          for (int j = 0; j < 4; ++j) have[j] = t0 + j <= ty1 ? (uint32_t)__ldca(p + (size_t)j * nw) : m;
 #pragma unroll
-          for (int j = 0; j < 8; ++j)
+          for (int j = 0; j < 4; ++j)
             if ((have[j] & m) != m) atomicOr(p + (size_t)j * nw, (int)m);
         }
       }
@@ -307,25 +314,27 @@ __global__ void __launch_bounds__(kBinThreads) bin_faces_kernel(Scene s, int set
       atomicOr(s.view_flag + b, 1);
     }
   }
-  __syncthreads();
-  // one global atomic per distinct bin of this CTA, each from its own thread
-  for (int t = tid; t < kBinHT; t += kBinThreads) {
-    const uint32_t ci = sm.keys[t];
-    if (ci != kBinEmpty) {
-      const int pos = atomicAdd(s.cnt + ci, sm.vals[t]);
-      if (FILL) sm.vals[t] = pos + s.off[ci];
+  if constexpr (AGG) {
+    __syncthreads();
+    // one global atomic per distinct bin of this CTA, each from its own thread
+    for (int t = tid; t < kBinHT; t += kBinThreads) {
+      const uint32_t ci = sm.keys[t];
+      if (ci != kBinEmpty) {
+        const int pos = atomicAdd(s.cnt + ci, sm.vals[t]);
+        if (FILL) sm.vals[t] = pos + s.off[ci];
+      }
     }
-  }
-  if (!FILL) return;
-  __syncthreads();
+    if (!FILL) return;
+    __syncthreads();
 #pragma unroll
-  for (int set = 0; set < 2; ++set) {
-    const int4 e = make_int4(f, r[set].x_lo | (r[set].x_hi << 16), r[set].y_lo | (r[set].y_hi << 16), 0);
-    int4* dst = s.entries + (size_t)set * 4 * s.NF + 4 * fbase;
+    for (int set = 0; set < 2; ++set) {
+      const int4 e = make_int4(f, r[set].x_lo | (r[set].x_hi << 16), r[set].y_lo | (r[set].y_hi << 16), 0);
+      int4* dst = s.entries + (size_t)set * 4 * s.NF + 4 * fbase;
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const int w = where[set][k];
-      if (sp[set].has && w >= 0) dst[sm.vals[w >> 16] + (w & 0xffff)] = e;
+      for (int k = 0; k < 4; ++k) {
+        const int w = where[set][k];
+        if (sp[set].has && w >= 0) dst[sm.vals[w >> 16] + (w & 0xffff)] = e;
+      }
     }
   }
 }
@@ -1724,9 +1733,13 @@ int build_bins(const Scene& s, int sets, cudaStream_t st) {
   if (e != cudaSuccess) return (int)e;
   if (s.NF > 0) {
     const unsigned blocks = (unsigned)((s.NF + kBinThreads - 1) / kBinThreads);
-    bin_faces_kernel<false><<<blocks, kBinThreads, 0, st>>>(s, sets);
+    // dense meshes (tens of faces per 16x16 tile) hammer a few counters: aggregate per CTA
+    const bool agg = s.NF / s.B >= (int64_t)32 * s.ntx[0] * s.nty[0];
+    if (agg) bin_faces_kernel<false, true><<<blocks, kBinThreads, 0, st>>>(s, sets);
+    else bin_faces_kernel<false, false><<<blocks, kBinThreads, 0, st>>>(s, sets);
     scan_bins_kernel<<<2 * s.B, 1024, 0, st>>>(s);
-    bin_faces_kernel<true><<<blocks, kBinThreads, 0, st>>>(s, sets);
+    if (agg) bin_faces_kernel<true, true><<<blocks, kBinThreads, 0, st>>>(s, sets);
+    else bin_faces_kernel<true, false><<<blocks, kBinThreads, 0, st>>>(s, sets);
   }
   return (int)cudaGetLastError();
 }
@@ -1847,16 +1860,20 @@ int dibr_b200_backward(int batch, int num_faces, int height, int width, int feat
                        const float* face_vertices_image, const float* face_features,
                        float multiplier, float eps, float sigmainv, float boxlen_m, int knum,
                        float* grad_face_vertices_image, float* grad_face_features, void* workspace,
-                       size_t workspace_bytes_, int bins_valid, dibr_b200_stream_t stream) {
+                       size_t workspace_bytes_, int flags, dibr_b200_stream_t stream) {
   const int64_t NF = (int64_t)batch * num_faces;
+  const bool bins_valid = (flags & DIBR_B200_BINS_VALID) != 0;
   int rc = check_dims(batch, NF, height, width);
   if (rc) return rc;
   if (!face_idx || !grad_face_vertices_image || num_faces < 0 || feat_dim < 0) return DIBR_B200_EINVAL;
   if (num_faces > 0 && !face_vertices_image) return DIBR_B200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
-  cudaError_t e = cudaMemsetAsync(grad_face_vertices_image, 0, (size_t)NF * 6 * sizeof(float), st);
-  if (e != cudaSuccess) return (int)e;
-  if (grad_face_features && feat_dim > 0) {
+  cudaError_t e = cudaSuccess;
+  if (!(flags & DIBR_B200_ACCUMULATE)) {
+    e = cudaMemsetAsync(grad_face_vertices_image, 0, (size_t)NF * 6 * sizeof(float), st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (grad_face_features && feat_dim > 0 && (grad_features || !(flags & DIBR_B200_ACCUMULATE))) {
     e = cudaMemsetAsync(grad_face_features, 0, (size_t)NF * 3 * feat_dim * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
   }

@@ -6,11 +6,17 @@ communication: rank r renders views [start, stop).  The only exchange is an
 all-gather of the per-view gradients after backward
 (``torch.distributed.all_gather_into_tensor`` — NCCL over NVLink on GPUs, gloo in
 the CPU tests).  One process per GPU; nothing here touches the kernels.
+
+``ChunkedGradAllGather`` hides that exchange behind the compute: the rank's views
+are rendered in a few view-chunks, and the gradients of chunk i travel (async
+collective on the process group's own stream) while chunk i+1 is rasterized, so
+only the last chunk's transfer is exposed (SURVEY.md §8e "chunked backward").
 """
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_range", "shard_views", "all_gather_view_grads"]
+__all__ = ["shard_range", "shard_views", "all_gather_view_grads", "chunk_ranges",
+           "ChunkedGradAllGather", "OverlappedGradAllGather"]
 
 
 def shard_range(batch, rank, world_size):
@@ -57,3 +63,117 @@ def all_gather_view_grads(local_grads, batch, group=None):
             full = torch.cat([buf[r * m:r * m + sizes[r]] for r in range(world)], 0)
         outs.append(full)
     return outs
+
+
+def chunk_ranges(views, chunks):
+    """Splits `views` local views into at most `chunks` contiguous [start, stop) pieces."""
+    chunks = max(1, min(int(chunks), views))
+    return [shard_range(views, c, chunks) for c in range(chunks)]
+
+
+class ChunkedGradAllGather:
+    """All-gather of per-view gradients, one view-chunk at a time, overlapped with compute.
+
+    Every rank owns ``local_views`` views (equal shards).  After the backward of
+    local views [c0, c1) call ``submit(c0, c1, [g_fvi_chunk, g_ff_chunk, ...])``: an
+    asynchronous all-gather of that chunk starts and the caller goes on with the
+    next chunk.  ``finish()`` makes the current stream wait for all of them and
+    returns the full tensors, rank-major: entry ``r * local_views + v`` is view v of
+    rank r - the layout ``all_gather_view_grads`` produces in one call.
+    """
+
+    def __init__(self, local_views, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.local_views = int(local_views)
+        self.full = None
+        self.pending = []
+
+    def submit(self, c0, c1, grads):
+        if not (0 <= c0 < c1 <= self.local_views):
+            raise ValueError(f"chunk [{c0}, {c1}) outside the {self.local_views} local views")
+        grads = [g.contiguous() for g in grads]
+        for g in grads:
+            if g.shape[0] != c1 - c0:
+                raise ValueError(f"chunk gradient has {g.shape[0]} views, chunk [{c0}, {c1}) has {c1 - c0}")
+        if self.full is None:
+            self.full = [torch.empty((self.world, self.local_views) + tuple(g.shape[1:]),
+                                     dtype=g.dtype, device=g.device) for g in grads]
+        for full, g in zip(self.full, grads):
+            # one contiguous landing buffer per chunk; copied to its rank-major place in finish()
+            buf = torch.empty((self.world * (c1 - c0),) + tuple(g.shape[1:]), dtype=g.dtype, device=g.device)
+            work = dist.all_gather_into_tensor(buf, g, group=self.group, async_op=True)
+            self.pending.append((work, full, buf, c0, c1, g))
+
+    def finish(self):
+        if self.full is None:
+            raise RuntimeError("ChunkedGradAllGather.finish() before any submit()")
+        for work, full, buf, c0, c1, _ in self.pending:
+            work.wait()                       # the current stream waits; the host does not block on CUDA
+            full[:, c0:c1].copy_(buf.view((self.world, c1 - c0) + tuple(buf.shape[1:])))
+        self.pending = []
+        out = [f.reshape((self.world * self.local_views,) + tuple(f.shape[2:])) for f in self.full]
+        self.full = None
+        return out
+
+
+class OverlappedGradAllGather:
+    """All-gather of the two DIB-R gradients with most of the transfer hidden behind the
+    backward itself: ``grad_face_features`` (60 % of the bytes at D = 3) is final as soon
+    as the rasterize branch of the fused backward has run, so its all-gather is started
+    there (asynchronously, on the process group's stream) and travels while the soft-mask
+    branch computes; ``grad_face_vertices_image`` follows at the end.
+
+        with OverlappedGradAllGather(batch) as gather:
+            torch.autograd.backward([feat, soft_mask], [g_feat, g_mask])
+        full_g_fvi, full_g_ff = gather.finish(face_vertices_image.grad)
+
+    Equal shards only (``batch`` = world size x local views).  Works the same through
+    ``kaolin_b200.render.mesh._host.backward`` (the C-ABI call).
+    """
+
+    def __init__(self, batch, group=None):
+        self.group = group
+        self.world = dist.get_world_size(group)
+        if batch % self.world:
+            raise ValueError(f"batch {batch} is not divisible by the world size {self.world}")
+        self.batch = int(batch)
+        self.work = None
+        self.full_ff = None
+        self.local_ff = None
+        self._prev = None
+
+    def _on_feature_grad(self, g_ff):
+        if self.work is not None:
+            raise RuntimeError("OverlappedGradAllGather covers one backward call")
+        if g_ff.shape[0] * self.world != self.batch:
+            raise ValueError(f"local gradient has {g_ff.shape[0]} views, expected {self.batch // self.world}")
+        self.local_ff = g_ff
+        self.full_ff = torch.empty((self.batch,) + tuple(g_ff.shape[1:]), dtype=g_ff.dtype, device=g_ff.device)
+        self.work = dist.all_gather_into_tensor(self.full_ff, g_ff, group=self.group, async_op=True)
+
+    def __enter__(self):
+        from .render.mesh import _host
+        self._prev = _host.FEATURE_GRAD_HOOK
+        _host.FEATURE_GRAD_HOOK = self._on_feature_grad
+        return self
+
+    def __exit__(self, *exc):
+        from .render.mesh import _host
+        _host.FEATURE_GRAD_HOOK = self._prev
+        return False
+
+    def finish(self, g_fvi, g_ff=None):
+        """Gathers ``g_fvi`` and returns (full_g_fvi, full_g_ff).  If the backward did not go
+        through the hook (e.g. only one of the two output gradients was given), pass the
+        local ``g_ff`` and it is gathered here."""
+        full_fvi = all_gather_view_grads([g_fvi], self.batch, self.group)[0]
+        if self.work is not None:
+            self.work.wait()
+            full_ff = self.full_ff
+        elif g_ff is not None:
+            full_ff = all_gather_view_grads([g_ff], self.batch, self.group)[0]
+        else:
+            raise RuntimeError("no feature gradient was produced inside the context and none was passed")
+        self.work = self.full_ff = self.local_ff = None
+        return full_fvi, full_ff

@@ -85,6 +85,22 @@ def forward(mode, height, width, fvz, fvi, ff, fnz, valid_u8, multiplier, eps,
     return feat, idx, wts, soft, ws
 
 
+# Called as hook(g_ff) between the two branches of a fused backward, when set (see
+# kaolin_b200.multi_gpu.OverlappedGradAllGather): grad_face_features is final after the
+# rasterize branch, so its all-gather can travel while the soft-mask branch runs.
+FEATURE_GRAD_HOOK = None
+
+
+def _backward_call(B, F, height, width, D, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps,
+                   sigmainv, boxlen_m, knum, g_fvi, g_ff, ws, ws_bytes, flags, dev):
+    with torch.cuda.device(dev):
+        st = _lib.lib().dibr_b200_backward(
+            B, F, height, width, D, ptr(g_feat), ptr(g_soft), ptr(face_idx), ptr(wts), ptr(soft),
+            ptr(fvi), ptr(ff), float(multiplier), float(eps), float(sigmainv), float(boxlen_m),
+            int(knum), ptr(g_fvi), ptr(g_ff), ptr(ws), ws_bytes, int(flags), stream_ptr(dev))
+    _lib.check(st, "dibr_b200_backward")
+
+
 def backward(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps,
              sigmainv, boxlen_m, knum, ws, bins_valid):
     dev = fvi.device
@@ -99,11 +115,16 @@ def backward(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multip
             ws = workspace(B, B * F, height, width, dev)
             bins_valid = False
         ws_bytes = ws.numel()
-    with torch.cuda.device(dev):
-        st = _lib.lib().dibr_b200_backward(
-            B, F, height, width, D, ptr(g_feat), ptr(g_soft), ptr(face_idx), ptr(wts), ptr(soft),
-            ptr(fvi), ptr(ff), float(multiplier), float(eps), float(sigmainv), float(boxlen_m),
-            int(knum), ptr(g_fvi), ptr(g_ff), ptr(ws), ws_bytes, int(bool(bins_valid)),
-            stream_ptr(dev))
-    _lib.check(st, "dibr_b200_backward")
+    flags = _lib.BINS_VALID if bins_valid else 0
+    hook = FEATURE_GRAD_HOOK
+    if hook is not None and g_feat is not None and g_soft is not None and D > 0:
+        # two calls: rasterize branch (g_ff final -> hook), then the soft-mask branch added on top
+        _backward_call(B, F, height, width, D, g_feat, None, face_idx, wts, None, fvi, ff, multiplier, eps,
+                       sigmainv, boxlen_m, knum, g_fvi, g_ff, None, 0, 0, dev)
+        hook(g_ff)
+        _backward_call(B, F, height, width, D, None, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps,
+                       sigmainv, boxlen_m, knum, g_fvi, None, ws, ws_bytes, flags | _lib.ACCUMULATE, dev)
+    else:
+        _backward_call(B, F, height, width, D, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps,
+                       sigmainv, boxlen_m, knum, g_fvi, g_ff, ws, ws_bytes, flags, dev)
     return g_fvi, g_ff

@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from kaolin_b200.multi_gpu import shard_range, shard_views, all_gather_view_grads
+from kaolin_b200.multi_gpu import (shard_range, shard_views, all_gather_view_grads, chunk_ranges,
+                                   ChunkedGradAllGather, OverlappedGradAllGather)
 
 
 def _fake_grads(batch, faces):
@@ -48,3 +49,68 @@ def test_shard_ranges_partition_the_batch():
             assert max(sizes) - min(sizes) <= 1
     with pytest.raises(ValueError):
         shard_range(4, 2, 2)
+
+
+def _chunk_worker(rank, world, batch, chunks, port, ok):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g, f = _fake_grads(batch, 5)
+        lg, lf = shard_views([g, f], rank, world)
+        gather = ChunkedGradAllGather(lg.shape[0])
+        for c0, c1 in chunk_ranges(lg.shape[0], chunks):
+            gather.submit(c0, c1, [lg[c0:c1].clone(), lf[c0:c1].clone()])
+        full_g, full_f = gather.finish()
+        ref_g, ref_f = all_gather_view_grads([lg.clone(), lf.clone()], batch)
+        ok[rank] = int(torch.equal(full_g, g) and torch.equal(full_f, f)
+                       and torch.equal(full_g, ref_g) and torch.equal(full_f, ref_f))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch,chunks", [(8, 4), (6, 2), (4, 8)])
+def test_two_rank_gloo_chunked_gather_equals_single_gather(batch, chunks):
+    ok = mp.get_context("spawn").Array("i", [0, 0])
+    port = 31500 + (os.getpid() % 2000) + batch * 8 + chunks
+    mp.spawn(_chunk_worker, args=(2, batch, chunks, port, ok), nprocs=2, join=True)
+    assert list(ok) == [1, 1]
+
+
+def test_chunk_ranges_cover_the_views():
+    for views in (1, 5, 32):
+        for chunks in (1, 3, 4, 64):
+            spans = chunk_ranges(views, chunks)
+            assert spans[0][0] == 0 and spans[-1][1] == views and len(spans) == min(chunks, views)
+            assert all(e > s for s, e in spans)
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(len(spans) - 1))
+
+
+def _overlap_worker(rank, world, batch, port, ok):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from kaolin_b200.render.mesh import _host
+        g, f = _fake_grads(batch, 5)
+        lg, lf = shard_views([g, f], rank, world)
+        with OverlappedGradAllGather(batch) as gather:
+            assert _host.FEATURE_GRAD_HOOK is not None
+            _host.FEATURE_GRAD_HOOK(lf.clone())      # what the fused backward does between its branches
+        assert _host.FEATURE_GRAD_HOOK is None
+        full_g, full_f = gather.finish(lg.clone())
+        # no hook call inside the context: the feature gradient is gathered in finish()
+        with OverlappedGradAllGather(batch) as gather2:
+            pass
+        full_g2, full_f2 = gather2.finish(lg.clone(), lf.clone())
+        ok[rank] = int(torch.equal(full_g, g) and torch.equal(full_f, f)
+                       and torch.equal(full_g2, g) and torch.equal(full_f2, f))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_overlapped_gather():
+    ok = mp.get_context("spawn").Array("i", [0, 0])
+    port = 33500 + (os.getpid() % 2000)
+    mp.spawn(_overlap_worker, args=(2, 6, port, ok), nprocs=2, join=True)
+    assert list(ok) == [1, 1]

@@ -149,6 +149,32 @@ def test_baseline_configs_vs_reference_cuda(name):
     assert e_xy <= 3e-5 and e_ff <= 3e-5
 
 
+def test_two_call_backward_with_feature_grad_hook_equals_fused():
+    """dibr_b200_backward split at the branch boundary (DIBR_B200_ACCUMULATE; the hook the
+    multi-GPU overlap uses) gives the gradients of the single fused call."""
+    from kaolin_b200.render.mesh import _host
+    fvz, fvi, fnz = synthetic.icosphere_views(3, 4, seed=11)
+    B, F = fvz.shape[:2]
+    H, W = 160, 144
+    ff = synthetic.random_features(B, F, 3, seed=5)
+    gen = torch.Generator(device=DEV); gen.manual_seed(3)
+    g_feat = torch.rand((B, H, W, 3), device=DEV, generator=gen)
+    g_soft = torch.rand((B, H, W), device=DEV, generator=gen)
+    grads, seen = [], []
+    for hook in (None, lambda g: seen.append(g.clone())):
+        t_fvi, t_ff = T(fvi, True), T(ff, True)
+        feat, soft, idx = dibr_rasterization(H, W, T(fvz), t_fvi, t_ff, T(fnz))
+        prev, _host.FEATURE_GRAD_HOOK = _host.FEATURE_GRAD_HOOK, hook
+        try:
+            torch.autograd.backward([feat, soft], [g_feat, g_soft])
+        finally:
+            _host.FEATURE_GRAD_HOOK = prev
+        grads.append((N(t_fvi.grad), N(t_ff.grad)))
+    assert len(seen) == 1 and rel_err(N(seen[0]), grads[1][1]) == 0.0   # g_ff was final at the hook
+    assert rel_err(grads[1][0], grads[0][0]) <= 1e-6                      # float atomics: order only
+    assert rel_err(grads[1][1], grads[0][1]) <= 1e-6
+
+
 def test_composition_equals_separate_calls():
     """test_dibr.py:482-529: dibr_rasterization == rasterize + dibr_soft_mask, torch.equal."""
     fvz, fvi, fnz = synthetic.icosphere_views(3, 3, seed=7)
