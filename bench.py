@@ -56,6 +56,9 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-ref-cuda", action="store_true")
     p.add_argument("--ref-cuda-views", type=int, default=2)
+    p.add_argument("--features", default="fp32", choices=["fp32", "bf16"],
+                   help="storage of face_features / features / grad_features (arithmetic is fp32 either "
+                        "way); BASELINE configs[3] names bf16, the reference itself only has fp32/fp64")
     p.add_argument("--chunks", type=int, default=1,
                    help="N > 1: 1 = the all-gather of grad_face_features overlaps the soft-mask branch of "
                         "the backward (default); k > 1 = k view-chunks per step, chunk i's all-gather "
@@ -223,10 +226,12 @@ def run_ours(args):
 
     B, F, H, W, D, fvz, fvi, fnz, ff = make_scene(args.workload, rank)
     pin = lambda a: torch.from_numpy(a).pin_memory()
-    h_fvz, h_fvi, h_fnz, h_ff = pin(fvz), pin(fvi), pin(fnz), pin(ff)
+    fdt = torch.bfloat16 if args.features == "bf16" else torch.float32
+    h_fvz, h_fvi, h_fnz = pin(fvz), pin(fvi), pin(fnz)
+    h_ff = torch.from_numpy(ff).to(fdt).pin_memory()
     d_fvz, d_fvi, d_fnz, d_ff = (t.to(dev) for t in (h_fvz, h_fvi, h_fnz, h_ff))
     gen = torch.Generator(device=dev); gen.manual_seed(4321 + rank)
-    g_feat = torch.rand((B, H, W, D), device=dev, generator=gen)
+    g_feat = torch.rand((B, H, W, D), device=dev, generator=gen).to(fdt)
     g_soft = torch.rand((B, H, W), device=dev, generator=gen)
     boxlen_m = BOXLEN * MULT
     mode = _lib.RASTER | _lib.SOFT_MASK
@@ -317,7 +322,7 @@ def run_ours(args):
         bufs[1].requires_grad_(True); bufs[2].requires_grad_(True)
         dev_in.append(bufs)
     host_out = [(torch.empty((B, F, 3, 2), dtype=torch.float32).pin_memory(),
-                 torch.empty((B, F, 3, D), dtype=torch.float32).pin_memory(),
+                 torch.empty((B, F, 3, D), dtype=fdt).pin_memory(),
                  torch.empty((1,), dtype=torch.float32).pin_memory()) for _ in range(NB)]
     ev_free = [None] * NB      # device inputs of slot consumed by compute
     ev_read = [None] * NB      # host outputs of slot downloaded
@@ -411,13 +416,13 @@ def run_ours(args):
         return
 
     peak, peak_src = peaks()
-    A = algorithmic_bytes(B, F, H, W, D)
+    A = algorithmic_bytes(B, F, H, W, D, s=2 if args.features == "bf16" else 4)
     ach = A["bwd_raster"] / (raster_bwd_ms * 1e-3) / 1e9
     traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel (ncu --set full)
     try:
         prof = json.load(open(os.path.join(ROOT, "profiles", "r1_kernels.json")))
         for name, e in prof.items():
-            if "raster_bwd_kernel" in name and args.workload == "c4_shard":
+            if "raster_bwd_kernel" in name and args.workload == "c4_shard" and args.features == "fp32":
                 traffic = e.get("dram_traffic_bytes")
     except Exception:
         traffic = None
@@ -443,7 +448,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "vertex_jitter": WORKLOADS[args.workload][5],
                    "views_per_gpu": B, "faces_per_view": F, "height": H,
-                   "width": W, "feat_dim": D, "features": "fp32", "knum": KNUM, "sigmainv": SIGMAINV,
+                   "width": W, "feat_dim": D, "features": args.features, "knum": KNUM, "sigmainv": SIGMAINV,
                    "boxlen": BOXLEN, "covered_fraction": covered,
                    "parallelism": (f"views sharded x{world}; NCCL all-gather of per-view grads, "
                                    + ("grad_face_features' gather overlapped with the soft-mask backward"
@@ -489,7 +494,8 @@ def time_reference_cuda(args, dev, B, F, H, W, D, d_fvz, d_fvi, d_ff, d_fnz, g_f
         if not ref_cuda.available():
             return {"unavailable": "oracle/_ref/kaolin_ref_C.so not present"}
         v = max(1, min(B, args.ref_cuda_views))
-        a = (d_fvz[:v], d_fvi[:v], d_ff[:v], d_fnz[:v], g_feat[:v].contiguous(), g_soft[:v].contiguous())
+        a = (d_fvz[:v], d_fvi[:v], d_ff[:v].float(), d_fnz[:v], g_feat[:v].float().contiguous(),
+             g_soft[:v].contiguous())
         ref_cuda.dibr_forward_backward(H, W, *a, SIGMAINV, BOXLEN, KNUM)
         torch.cuda.synchronize()
         n = 3

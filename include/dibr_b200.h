@@ -111,6 +111,33 @@ int dibr_b200_backward(
     void* workspace, size_t workspace_bytes, int flags, dibr_b200_stream_t stream);
 
 /*
+ * bf16 feature storage (BASELINE.json configs[3], "bf16 features"; an extension - the
+ * reference dispatches float/double only, rasterization_cuda.cu:218): same as
+ * dibr_b200_forward / dibr_b200_backward except that face_features (B,F,3,D),
+ * interpolated_features (B,H,W,D) and grad_features (B,H,W,D) hold bfloat16 bit patterns.
+ * Arithmetic is the fp32 arithmetic of the fp32 entry points on the upcast values; the
+ * interpolated feature is rounded to nearest-even once, on store, so it equals the fp32
+ * entry point's output converted to bf16.  Geometry, weights, soft mask and BOTH output
+ * gradients (fp32 accumulation) stay fp32.
+ */
+int dibr_b200_forward_bf16(
+    int batch, int num_faces, int height, int width, int feat_dim,
+    const float* face_vertices_z, const float* face_vertices_image,
+    const uint16_t* face_features, const float* face_normals_z, const uint8_t* valid_faces,
+    float multiplier, float eps, int mode, float sigmainv, float boxlen_m, int knum,
+    uint16_t* interpolated_features, int64_t* face_idx, float* output_weights, float* soft_mask,
+    void* workspace, size_t workspace_bytes, dibr_b200_stream_t stream);
+
+int dibr_b200_backward_bf16(
+    int batch, int num_faces, int height, int width, int feat_dim,
+    const uint16_t* grad_features, const float* grad_soft_mask,
+    const int64_t* face_idx, const float* output_weights, const float* soft_mask,
+    const float* face_vertices_image, const uint16_t* face_features,
+    float multiplier, float eps, float sigmainv, float boxlen_m, int knum,
+    float* grad_face_vertices_image, float* grad_face_features,
+    void* workspace, size_t workspace_bytes, int flags, dibr_b200_stream_t stream);
+
+/*
  * Operator: kaolin::packed_rasterize_forward_cuda
  * (kaolin/csrc/render/mesh/rasterization.h:23-32, rasterization.cpp:49-104).
  * Packed valid faces of all meshes; coordinates already multiplied; tight bboxes

@@ -39,6 +39,10 @@ SIGNATURES = {
                                _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dibr_b200_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _f, _f, _f, _f, _i, _vp, _vp, _vp, _sz, _i, _vp]),
+    "dibr_b200_forward_bf16": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _f, _f, _i,
+                                    _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dibr_b200_backward_bf16": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                     _f, _f, _f, _f, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "dibr_b200_packed_rasterize_forward": (_i, [_i, _i64, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f,
                                                 _vp, _vp, _vp, _vp, _sz, _vp]),
     "dibr_b200_rasterize_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f,

@@ -25,6 +25,7 @@
 // on the face id (rasterize branch) and a dense stream over the cached pairs
 // (soft-mask branch; tiles outside the cache are recomputed).
 #include <cuda_runtime.h>
+#include <cuda_bf16.h>
 #include <type_traits>
 #include <stdint.h>
 
@@ -1073,20 +1074,38 @@ __device__ __forceinline__ TileCtx tile_ctx_from_linear(const Scene& s, int t) {
 }
 
 // ---------------------------------------------------------------------------
+// Feature storage type FT: float, or __nv_bfloat16 (BASELINE configs[3] "bf16 features":
+// face_features, interpolated_features and their upstream gradient are bf16 in HBM; all
+// arithmetic stays fp32 on the upcast values, the result is rounded once on store, and
+// grad_face_features is accumulated in fp32).  Geometry is always fp32.
+template <typename FT> struct Feat;
+template <> struct Feat<float> {
+  static __device__ __forceinline__ float ld(const float* p) { return __ldg(p); }
+  static __device__ __forceinline__ float ld_stream(const float* p) { return __ldcs(p); }
+  static __device__ __forceinline__ void st(float* p, float v) { *p = v; }
+};
+template <> struct Feat<__nv_bfloat16> {
+  static __device__ __forceinline__ float ld(const __nv_bfloat16* p) { return __bfloat162float(__ldg(p)); }
+  static __device__ __forceinline__ float ld_stream(const __nv_bfloat16* p) { return __bfloat162float(__ldcs(p)); }
+  static __device__ __forceinline__ void st(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+};
+
+// ---------------------------------------------------------------------------
 // Forward tile kernel.
 struct FwdArgs {
   Scene s;
   RasterConst rc;
   int D;
-  const float* feat;        // (NF,3,D)
+  const void* feat;         // (NF,3,D) FT
   float sigmainv; int K;
   int cache;                // fill the soft-mask hit cache
   int from_fb;              // soft_tiles_fwd_kernel: walk fb_list instead of band_list
-  float* out_feat; int64_t* idx; float* out_w; float* out_soft;  // idx: output if RASTER else input
+  void* out_feat;           // (B,H,W,D) FT
+  int64_t* idx; float* out_w; float* out_soft;  // idx: output if RASTER else input
   SoftFwdOut kl;
 };
 
-template <bool RASTER, bool SOFT, bool KLISTS>
+template <bool RASTER, bool SOFT, bool KLISTS, typename FT>
 __global__ void __launch_bounds__(kThreads, 6) dibr_tile_fwd_kernel(const __grid_constant__ FwdArgs a) {
   __shared__ __align__(128) RasterSmem sm;
   const Scene& s = a.s;
@@ -1105,22 +1124,25 @@ __global__ void __launch_bounds__(kThreads, 6) dibr_tile_fwd_kernel(const __grid
       a.idx[c.pix] = (int64_t)o.f;
       float* wp = a.out_w + c.pix * 3;
       wp[0] = o.w0; wp[1] = o.w1; wp[2] = o.w2;
-      float* fp = a.out_feat + c.pix * a.D;
+      FT* fp = static_cast<FT*>(a.out_feat) + c.pix * a.D;
+      const FT* feat = static_cast<const FT*>(a.feat);
       if (a.D == 3) {  // the DIB-R tutorial shape (uv + mask), fully unrolled
         float r[3] = {0.f, 0.f, 0.f};
         if (o.f >= 0) {
-          const float* ff = a.feat + (c.fbase + o.f) * 9;
+          const FT* ff = feat + (c.fbase + o.f) * 9;
 #pragma unroll
           for (int d = 0; d < 3; ++d)
-            r[d] = raster_interp(__ldg(ff + d), __ldg(ff + 3 + d), __ldg(ff + 6 + d), o.w0, o.w1, o.w2);
+            r[d] = raster_interp(Feat<FT>::ld(ff + d), Feat<FT>::ld(ff + 3 + d), Feat<FT>::ld(ff + 6 + d),
+                                 o.w0, o.w1, o.w2);
         }
-        fp[0] = r[0]; fp[1] = r[1]; fp[2] = r[2];
+        Feat<FT>::st(fp, r[0]); Feat<FT>::st(fp + 1, r[1]); Feat<FT>::st(fp + 2, r[2]);
       } else if (o.f >= 0) {
-        const float* ff = a.feat + (c.fbase + o.f) * 3 * a.D;
+        const FT* ff = feat + (c.fbase + o.f) * 3 * a.D;
         for (int d = 0; d < a.D; ++d)
-          fp[d] = raster_interp(__ldg(ff + d), __ldg(ff + a.D + d), __ldg(ff + 2 * a.D + d), o.w0, o.w1, o.w2);
+          Feat<FT>::st(fp + d, raster_interp(Feat<FT>::ld(ff + d), Feat<FT>::ld(ff + a.D + d),
+                                             Feat<FT>::ld(ff + 2 * a.D + d), o.w0, o.w1, o.w2));
       } else {
-        for (int d = 0; d < a.D; ++d) fp[d] = 0.f;
+        for (int d = 0; d < a.D; ++d) Feat<FT>::st(fp + d, 0.f);
       }
     }
   } else {
@@ -1475,13 +1497,15 @@ __device__ __forceinline__ void reduce_peers(unsigned peers, float (&v)[N]) {
 struct RasterBwdArgs {
   int B, H, W, F, D;
   int ntx, nty;
-  const float* grad_feat; const int64_t* idx; const float* w; const float* xy; const float* feat;
+  const void* grad_feat; const int64_t* idx; const float* w; const float* xy; const void* feat;  // FT
   float eps;
   float* grad_xy; float* grad_feat_out;
 };
 
-template <int DT>  // DT > 0: feature dim known at compile time; 0: runtime loop
+template <int DT, typename FT>  // DT > 0: feature dim known at compile time; 0: runtime loop
 __global__ void __launch_bounds__(kThreads, 6) raster_bwd_kernel(const __grid_constant__ RasterBwdArgs a) {
+  const FT* grad_feat = static_cast<const FT*>(a.grad_feat);
+  const FT* feat = static_cast<const FT*>(a.feat);
   const int tx = blockIdx.x, ty = blockIdx.y, b = blockIdx.z;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int px = tx * kTile + (((warp & 1) << 3) | (lane & 7));
@@ -1502,7 +1526,7 @@ __global__ void __launch_bounds__(kThreads, 6) raster_bwd_kernel(const __grid_co
     w0 = __ldcs(wp); w1 = __ldcs(wp + 1); w2 = __ldcs(wp + 2);
     if (DT > 0) {
 #pragma unroll
-      for (int d = 0; d < DT; ++d) gpre[d] = __ldcs(a.grad_feat + pix * DT + d);
+      for (int d = 0; d < DT; ++d) gpre[d] = Feat<FT>::ld_stream(grad_feat + pix * DT + d);
     }
   }
   if (!__any_sync(kFull, f >= 0)) return;
@@ -1519,8 +1543,8 @@ __global__ void __launch_bounds__(kThreads, 6) raster_bwd_kernel(const __grid_co
   // lanes without a face get unique negative keys so they never merge
   const unsigned peers = __match_any_sync(kFull, cov ? (int)f : -1 - lane);
   const bool leader = (peers & ((1u << lane) - 1u)) == 0;
-  const float* gp = a.grad_feat + pix * D;
-  const float* cf = a.feat + face * 3 * D;
+  const FT* gp = grad_feat + pix * D;
+  const FT* cf = feat + face * 3 * D;
 
   if (DT > 0) {
     float v[6 + 3 * (DT > 0 ? DT : 1)];
@@ -1532,7 +1556,7 @@ __global__ void __launch_bounds__(kThreads, 6) raster_bwd_kernel(const __grid_co
       if (cov) {
         g = gpre[d];
         float t6[6];
-        raster_backward_feature(G, g, __ldg(cf + d), __ldg(cf + DT + d), __ldg(cf + 2 * DT + d), t6);
+        raster_backward_feature(G, g, Feat<FT>::ld(cf + d), Feat<FT>::ld(cf + DT + d), Feat<FT>::ld(cf + 2 * DT + d), t6);
 #pragma unroll
         for (int j = 0; j < 6; ++j) v[j] += t6[j];
       }
@@ -1555,9 +1579,9 @@ __global__ void __launch_bounds__(kThreads, 6) raster_bwd_kernel(const __grid_co
     for (int d = 0; d < D; ++d) {
       float g = 0.f;
       if (cov) {
-        g = gp[d];
+        g = Feat<FT>::ld_stream(gp + d);
         float t6[6];
-        raster_backward_feature(G, g, __ldg(cf + d), __ldg(cf + D + d), __ldg(cf + 2 * D + d), t6);
+        raster_backward_feature(G, g, Feat<FT>::ld(cf + d), Feat<FT>::ld(cf + D + d), Feat<FT>::ld(cf + 2 * D + d), t6);
 #pragma unroll
         for (int j = 0; j < 6; ++j) vx[j] += t6[j];
       }
@@ -1761,11 +1785,11 @@ unsigned persistent_grid(const Scene& s, Kernel kernel, size_t dyn_smem = 0) {
   return (unsigned)(ntiles < g ? ntiles : g);
 }
 
-template <bool R, bool S, bool K>
+template <bool R, bool S, bool K, typename FT = float>
 void launch_fwd(const FwdArgs& a0, cudaStream_t st) {
   FwdArgs a = a0;
   a.from_fb = 0;
-  dibr_tile_fwd_kernel<R, S, K><<<tile_grid(a.s), kThreads, 0, st>>>(a);
+  dibr_tile_fwd_kernel<R, S, K, FT><<<tile_grid(a.s), kThreads, 0, st>>>(a);
   if (S) {
     cudaFuncSetAttribute(soft_tiles_fwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(SoftSmem));
@@ -1783,14 +1807,15 @@ void launch_fwd(const FwdArgs& a0, cudaStream_t st) {
   }
 }
 
+template <typename FT>
 int launch_raster_bwd(const RasterBwdArgs& a, cudaStream_t st) {
   const dim3 grid((unsigned)a.ntx, (unsigned)a.nty, (unsigned)a.B);
   switch (a.D) {
-    case 1: raster_bwd_kernel<1><<<grid, kThreads, 0, st>>>(a); break;
-    case 2: raster_bwd_kernel<2><<<grid, kThreads, 0, st>>>(a); break;
-    case 3: raster_bwd_kernel<3><<<grid, kThreads, 0, st>>>(a); break;
-    case 4: raster_bwd_kernel<4><<<grid, kThreads, 0, st>>>(a); break;
-    default: raster_bwd_kernel<0><<<grid, kThreads, 0, st>>>(a); break;
+    case 1: raster_bwd_kernel<1, FT><<<grid, kThreads, 0, st>>>(a); break;
+    case 2: raster_bwd_kernel<2, FT><<<grid, kThreads, 0, st>>>(a); break;
+    case 3: raster_bwd_kernel<3, FT><<<grid, kThreads, 0, st>>>(a); break;
+    case 4: raster_bwd_kernel<4, FT><<<grid, kThreads, 0, st>>>(a); break;
+    default: raster_bwd_kernel<0, FT><<<grid, kThreads, 0, st>>>(a); break;
   }
   return (int)cudaGetLastError();
 }
@@ -1816,13 +1841,13 @@ size_t dibr_b200_workspace_bytes_cached(int batch, int64_t total_faces, int heig
          (size_t)cache_tiles * pool_block_bytes(knum);
 }
 
-int dibr_b200_forward(int batch, int num_faces, int height, int width, int feat_dim,
-                      const float* face_vertices_z, const float* face_vertices_image,
-                      const float* face_features, const float* face_normals_z,
-                      const uint8_t* valid_faces, float multiplier, float eps, int mode,
-                      float sigmainv, float boxlen_m, int knum, float* interpolated_features,
-                      int64_t* face_idx, float* output_weights, float* soft_mask, void* workspace,
-                      size_t workspace_bytes_, dibr_b200_stream_t stream) {
+static int forward_impl(int batch, int num_faces, int height, int width, int feat_dim,
+                        const float* face_vertices_z, const float* face_vertices_image,
+                        const void* face_features, const float* face_normals_z,
+                        const uint8_t* valid_faces, float multiplier, float eps, int mode,
+                        float sigmainv, float boxlen_m, int knum, void* interpolated_features,
+                        int64_t* face_idx, float* output_weights, float* soft_mask, void* workspace,
+                        size_t workspace_bytes_, dibr_b200_stream_t stream, bool bf16) {
   const int64_t NF = (int64_t)batch * num_faces;
   int rc = check_dims(batch, NF, height, width);
   if (rc) return rc;
@@ -1848,19 +1873,46 @@ int dibr_b200_forward(int batch, int num_faces, int height, int width, int feat_
   a.cache = soft ? 1 : 0;   // hits are cached while blocks last; other tiles go to fb_list
   a.out_feat = interpolated_features; a.idx = face_idx; a.out_w = output_weights; a.out_soft = soft_mask;
   a.kl = SoftFwdOut{nullptr, nullptr, nullptr};
-  if (raster && soft) launch_fwd<true, true, false>(a, st);
-  else if (raster) launch_fwd<true, false, false>(a, st);
+  if (raster && soft) { if (bf16) launch_fwd<true, true, false, __nv_bfloat16>(a, st); else launch_fwd<true, true, false>(a, st); }
+  else if (raster) { if (bf16) launch_fwd<true, false, false, __nv_bfloat16>(a, st); else launch_fwd<true, false, false>(a, st); }
   else launch_fwd<false, true, false>(a, st);
   return (int)cudaGetLastError();
 }
 
-int dibr_b200_backward(int batch, int num_faces, int height, int width, int feat_dim,
-                       const float* grad_features, const float* grad_soft_mask,
-                       const int64_t* face_idx, const float* output_weights, const float* soft_mask,
-                       const float* face_vertices_image, const float* face_features,
-                       float multiplier, float eps, float sigmainv, float boxlen_m, int knum,
-                       float* grad_face_vertices_image, float* grad_face_features, void* workspace,
-                       size_t workspace_bytes_, int flags, dibr_b200_stream_t stream) {
+int dibr_b200_forward(int batch, int num_faces, int height, int width, int feat_dim,
+                      const float* face_vertices_z, const float* face_vertices_image,
+                      const float* face_features, const float* face_normals_z,
+                      const uint8_t* valid_faces, float multiplier, float eps, int mode,
+                      float sigmainv, float boxlen_m, int knum, float* interpolated_features,
+                      int64_t* face_idx, float* output_weights, float* soft_mask, void* workspace,
+                      size_t workspace_bytes_, dibr_b200_stream_t stream) {
+  return forward_impl(batch, num_faces, height, width, feat_dim, face_vertices_z, face_vertices_image,
+                      face_features, face_normals_z, valid_faces, multiplier, eps, mode, sigmainv, boxlen_m,
+                      knum, interpolated_features, face_idx, output_weights, soft_mask, workspace,
+                      workspace_bytes_, stream, false);
+}
+
+int dibr_b200_forward_bf16(int batch, int num_faces, int height, int width, int feat_dim,
+                           const float* face_vertices_z, const float* face_vertices_image,
+                           const uint16_t* face_features, const float* face_normals_z,
+                           const uint8_t* valid_faces, float multiplier, float eps, int mode,
+                           float sigmainv, float boxlen_m, int knum, uint16_t* interpolated_features,
+                           int64_t* face_idx, float* output_weights, float* soft_mask, void* workspace,
+                           size_t workspace_bytes_, dibr_b200_stream_t stream) {
+  return forward_impl(batch, num_faces, height, width, feat_dim, face_vertices_z, face_vertices_image,
+                      face_features, face_normals_z, valid_faces, multiplier, eps, mode, sigmainv, boxlen_m,
+                      knum, interpolated_features, face_idx, output_weights, soft_mask, workspace,
+                      workspace_bytes_, stream, true);
+}
+
+
+static int backward_impl(int batch, int num_faces, int height, int width, int feat_dim,
+                         const void* grad_features, const float* grad_soft_mask,
+                         const int64_t* face_idx, const float* output_weights, const float* soft_mask,
+                         const float* face_vertices_image, const void* face_features,
+                         float multiplier, float eps, float sigmainv, float boxlen_m, int knum,
+                         float* grad_face_vertices_image, float* grad_face_features, void* workspace,
+                         size_t workspace_bytes_, int flags, dibr_b200_stream_t stream, bool bf16) {
   const int64_t NF = (int64_t)batch * num_faces;
   const bool bins_valid = (flags & DIBR_B200_BINS_VALID) != 0;
   int rc = check_dims(batch, NF, height, width);
@@ -1886,7 +1938,7 @@ int dibr_b200_backward(int batch, int num_faces, int height, int width, int feat
     a.grad_feat = grad_features; a.idx = face_idx; a.w = output_weights; a.xy = face_vertices_image;
     a.feat = face_features; a.eps = eps; a.grad_xy = grad_face_vertices_image;
     a.grad_feat_out = grad_face_features;
-    rc = launch_raster_bwd(a, st);
+    rc = bf16 ? launch_raster_bwd<__nv_bfloat16>(a, st) : launch_raster_bwd<float>(a, st);
     if (rc) return rc;
   }
   if (grad_soft_mask) {
@@ -1916,6 +1968,32 @@ int dibr_b200_backward(int batch, int num_faces, int height, int width, int feat
     return (int)cudaGetLastError();
   }
   return 0;
+}
+
+int dibr_b200_backward(int batch, int num_faces, int height, int width, int feat_dim,
+                       const float* grad_features, const float* grad_soft_mask,
+                       const int64_t* face_idx, const float* output_weights, const float* soft_mask,
+                       const float* face_vertices_image, const float* face_features,
+                       float multiplier, float eps, float sigmainv, float boxlen_m, int knum,
+                       float* grad_face_vertices_image, float* grad_face_features, void* workspace,
+                       size_t workspace_bytes_, int flags, dibr_b200_stream_t stream) {
+  return backward_impl(batch, num_faces, height, width, feat_dim, grad_features, grad_soft_mask, face_idx,
+                       output_weights, soft_mask, face_vertices_image, face_features, multiplier, eps,
+                       sigmainv, boxlen_m, knum, grad_face_vertices_image, grad_face_features, workspace,
+                       workspace_bytes_, flags, stream, false);
+}
+
+int dibr_b200_backward_bf16(int batch, int num_faces, int height, int width, int feat_dim,
+                            const uint16_t* grad_features, const float* grad_soft_mask,
+                            const int64_t* face_idx, const float* output_weights, const float* soft_mask,
+                            const float* face_vertices_image, const uint16_t* face_features,
+                            float multiplier, float eps, float sigmainv, float boxlen_m, int knum,
+                            float* grad_face_vertices_image, float* grad_face_features, void* workspace,
+                            size_t workspace_bytes_, int flags, dibr_b200_stream_t stream) {
+  return backward_impl(batch, num_faces, height, width, feat_dim, grad_features, grad_soft_mask, face_idx,
+                       output_weights, soft_mask, face_vertices_image, face_features, multiplier, eps,
+                       sigmainv, boxlen_m, knum, grad_face_vertices_image, grad_face_features, workspace,
+                       workspace_bytes_, flags, stream, true);
 }
 
 int dibr_b200_packed_rasterize_forward(int batch, int64_t total_faces, int height, int width,

@@ -16,6 +16,15 @@ def stream_ptr(device):
     return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
 
 
+FEATURE_DTYPES = (torch.float32, torch.bfloat16)   # storage of face_features / interpolated features
+
+
+def check_feature_dtype(func, name, t):
+    if t is not None and t.dtype not in FEATURE_DTYPES:
+        raise RuntimeError(f"\"{func}\" not implemented for '{str(t.dtype).replace('torch.', '')}' "
+                           f"({name}: kaolin_b200 stores features as float32 or bfloat16)")
+
+
 def check_tensors(func, named, dtype=torch.float32):
     """All tensors on the same CUDA device with the expected dtype (no CPU path)."""
     dev = None
@@ -71,13 +80,16 @@ def forward(mode, height, width, fvz, fvi, ff, fnz, valid_u8, multiplier, eps,
     D = 0 if ff is None else ff.shape[-1]
     raster = bool(mode & _lib.RASTER)
     soft_on = bool(mode & _lib.SOFT_MASK)
-    feat = torch.empty((B, height, width, D), dtype=torch.float32, device=dev) if raster else None
+    bf16 = ff is not None and ff.dtype == torch.bfloat16
+    feat = torch.empty((B, height, width, D), dtype=torch.bfloat16 if bf16 else torch.float32,
+                       device=dev) if raster else None
     wts = torch.empty((B, height, width, 3), dtype=torch.float32, device=dev) if raster else None
     idx = torch.empty((B, height, width), dtype=torch.int64, device=dev) if raster else face_idx_in
     soft = torch.empty((B, height, width), dtype=torch.float32, device=dev) if soft_on else None
     ws = workspace(B, B * F, height, width, dev, knum if soft_on else 0)
     with torch.cuda.device(dev):
-        st = _lib.lib().dibr_b200_forward(
+        fn = _lib.lib().dibr_b200_forward_bf16 if bf16 else _lib.lib().dibr_b200_forward
+        st = fn(
             B, F, height, width, D, ptr(fvz), ptr(fvi), ptr(ff), ptr(fnz), ptr(valid_u8),
             float(multiplier), float(eps), mode, float(sigmainv), float(boxlen_m), int(knum),
             ptr(feat), ptr(idx), ptr(wts), ptr(soft), ptr(ws), ws.numel(), stream_ptr(dev))
@@ -93,8 +105,12 @@ FEATURE_GRAD_HOOK = None
 
 def _backward_call(B, F, height, width, D, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps,
                    sigmainv, boxlen_m, knum, g_fvi, g_ff, ws, ws_bytes, flags, dev):
+    bf16 = ff is not None and ff.dtype == torch.bfloat16
+    if g_feat is not None and ff is not None and g_feat.dtype != ff.dtype:
+        raise RuntimeError(f"dibr_b200_backward: grad_features is {g_feat.dtype}, face_features is {ff.dtype}")
     with torch.cuda.device(dev):
-        st = _lib.lib().dibr_b200_backward(
+        fn = _lib.lib().dibr_b200_backward_bf16 if bf16 else _lib.lib().dibr_b200_backward
+        st = fn(
             B, F, height, width, D, ptr(g_feat), ptr(g_soft), ptr(face_idx), ptr(wts), ptr(soft),
             ptr(fvi), ptr(ff), float(multiplier), float(eps), float(sigmainv), float(boxlen_m),
             int(knum), ptr(g_fvi), ptr(g_ff), ptr(ws), ws_bytes, int(flags), stream_ptr(dev))
@@ -107,7 +123,8 @@ def backward(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multip
     B, F = fvi.shape[0], fvi.shape[1]
     D = 0 if ff is None else ff.shape[-1]
     g_fvi = torch.empty_like(fvi)
-    g_ff = torch.empty_like(ff) if ff is not None else None
+    # grad_face_features is accumulated (atomics) in fp32 whatever the storage type
+    g_ff = torch.empty(ff.shape, dtype=torch.float32, device=dev) if ff is not None else None
     if g_soft is None:
         ws, ws_bytes, bins_valid = None, 0, False   # the rasterize branch needs no scratch
     else:

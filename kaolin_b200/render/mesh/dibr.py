@@ -75,6 +75,7 @@ class DibrRasterizationB200(Function):
             multiplier, eps, sigmainv, boxlen_m, knum)
         ctx.save_for_backward(face_idx, wts, soft, fvi, ff)
         ctx.mark_non_differentiable(face_idx)
+        ctx.set_materialize_grads(False)   # no 8 B/pixel zero "gradient" for face_idx
         ctx.params = (height, width, multiplier, eps, sigmainv, boxlen_m, knum)
         ctx.ws = ws
         return feat, soft, face_idx
@@ -87,6 +88,7 @@ class DibrRasterizationB200(Function):
         g_soft = None if grad_soft_mask is None else grad_soft_mask.contiguous()
         g_fvi, g_ff = _host.backward(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff,
                                      multiplier, eps, sigmainv, boxlen_m, knum, ctx.ws, True)
+        g_ff = g_ff.to(ff.dtype)      # fp32 accumulation; autograd wants the input's dtype (bf16 features)
         return None, None, None, g_fvi, g_ff, None, None, None, None, None, None, None
 
 

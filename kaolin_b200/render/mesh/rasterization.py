@@ -31,6 +31,7 @@ class RasterizeB200(Function):
             _lib.RASTER, height, width, fvz, fvi, ff, None, valid_u8, multiplier, eps, 0., 0., 0)
         ctx.save_for_backward(face_idx, wts, fvi, ff)
         ctx.mark_non_differentiable(face_idx)
+        ctx.set_materialize_grads(False)   # no 8 B/pixel zero "gradient" for face_idx
         ctx.eps = eps
         ctx.hw = (height, width)
         return feat, face_idx
@@ -41,14 +42,17 @@ class RasterizeB200(Function):
         g = grad_interpolated_features.contiguous()
         g_fvi, g_ff = _host.backward(ctx.hw[0], ctx.hw[1], g, None, face_idx, wts, None, fvi, ff,
                                      1.0, ctx.eps, 0., 0., 0, None, False)
+        g_ff = g_ff.to(ff.dtype)      # fp32 accumulation; autograd wants the input's dtype (bf16 features)
         # the reference never produces a gradient for face_vertices_z (rasterization.py:370-371)
         return None, None, None, g_fvi, g_ff, None, None, None
 
 
 def _check_inputs(func, face_vertices_z, face_vertices_image, face_features):
     _host.check_tensors(func, [("face_vertices_z", face_vertices_z),
-                               ("face_vertices_image", face_vertices_image),
-                               ("face_features", face_features)])
+                               ("face_vertices_image", face_vertices_image)])
+    _host.check_tensors(func, [("face_vertices_z", face_vertices_z), ("face_features", face_features)],
+                        dtype=None)                       # same device; the dtype is checked next
+    _host.check_feature_dtype(func, "face_features", face_features)
     if face_vertices_z.dim() != 3 or face_vertices_z.shape[-1] != 3:
         raise RuntimeError(f"{func}: face_vertices_z must be of shape (batch_size, num_faces, 3)")
     B, F, _ = face_vertices_z.shape

@@ -175,6 +175,75 @@ def test_two_call_backward_with_feature_grad_hook_equals_fused():
     assert rel_err(grads[1][1], grads[0][1]) <= 1e-6
 
 
+def test_backward_through_one_output_only():
+    """Undefined output gradients are not materialised: backward through features only or the
+    soft mask only runs one branch, and the two add up to the gradient through both."""
+    fvz, fvi, fnz = synthetic.icosphere_views(2, 3, seed=13)
+    B, F = fvz.shape[:2]
+    H, W = 96, 112
+    ff = synthetic.random_features(B, F, 3, seed=6)
+    gen = torch.Generator(device=DEV); gen.manual_seed(4)
+    g_feat = torch.rand((B, H, W, 3), device=DEV, generator=gen)
+    g_soft = torch.rand((B, H, W), device=DEV, generator=gen)
+    out = {}
+    for which in ("feat", "soft", "both"):
+        t_fvi, t_ff = T(fvi, True), T(ff, True)
+        feat, soft, idx = dibr_rasterization(H, W, T(fvz), t_fvi, t_ff, T(fnz))
+        if which == "feat":
+            torch.autograd.backward([feat], [g_feat])
+        elif which == "soft":
+            torch.autograd.backward([soft], [g_soft])
+        else:
+            torch.autograd.backward([feat, soft], [g_feat, g_soft])
+        out[which] = (N(t_fvi.grad), None if t_ff.grad is None else N(t_ff.grad))
+    assert out["soft"][1] is None or not out["soft"][1].any()
+    assert rel_err(out["feat"][1], out["both"][1]) <= 1e-6
+    assert rel_err(out["feat"][0] + out["soft"][0], out["both"][0]) <= 1e-5
+    assert np.abs(out["soft"][0]).max() > 0 and np.abs(out["feat"][0]).max() > 0
+
+
+@pytest.mark.skipif(not ref_cuda.available(), reason="oracle/_ref (reference CUDA build) not present")
+@pytest.mark.parametrize("D", [3, 5])
+def test_bf16_feature_storage_vs_reference_cuda(D):
+    """BASELINE configs[3]: bf16 face_features / features / grad_features, fp32 arithmetic.
+    The interpolated features equal the reference's fp32 result (on the same bf16-rounded
+    inputs) rounded once to bf16; everything geometric is unchanged."""
+    from kaolin_b200.render.mesh import _host
+    fvz, fvi, fnz = synthetic.icosphere_views(2, 4, seed=21)
+    B, F = fvz.shape[:2]
+    H, W = 192, 176
+    ff16 = T(synthetic.random_features(B, F, D, seed=8)).to(torch.bfloat16)
+    gen = torch.Generator(device=DEV); gen.manual_seed(9)
+    g_feat16 = torch.rand((B, H, W, D), device=DEV, generator=gen).to(torch.bfloat16)
+    g_soft = torch.rand((B, H, W), device=DEV, generator=gen)
+    t_fvz, t_fnz = T(fvz), T(fnz)
+    t_fvi, t_ff = T(fvi, True), ff16.clone().requires_grad_(True)
+    feat, soft, idx = dibr_rasterization(H, W, t_fvz, t_fvi, t_ff, t_fnz)
+    assert feat.dtype == torch.bfloat16 and soft.dtype == torch.float32
+    torch.autograd.backward([feat, soft], [g_feat16, g_soft])
+    assert t_ff.grad.dtype == torch.bfloat16 and t_fvi.grad.dtype == torch.float32
+    r = ref_cuda.dibr_forward_backward(H, W, t_fvz, t_fvi.detach(), ff16.float(), t_fnz,
+                                       g_feat16.float(), g_soft)
+    assert torch.equal(idx, r["face_idx"])
+    assert torch.equal(soft, r["soft_mask"])
+    assert torch.equal(feat, r["features"].to(torch.bfloat16))            # one rounding, on store
+    assert rel_err(N(t_fvi.grad), N(r["grad_fvi"])) <= 3e-5
+    assert rel_err(N(t_ff.grad.float()), N(r["grad_ff"])) <= 2.0 ** -8      # bf16 rounding of the result
+    # the C ABI returns the fp32 accumulation itself
+    feat2, idx2, wts2, soft2, ws = _host.forward(3, H, W, t_fvz, t_fvi.detach(), ff16, t_fnz, None, 1000., 1e-8,
+                                                 7000., 0.02 * 1000., 30)
+    g_fvi, g_ff = _host.backward(H, W, g_feat16, g_soft, idx2, wts2, soft2, t_fvi.detach(), ff16, 1000., 1e-8,
+                                 7000., 0.02 * 1000., 30, ws, True)
+    assert g_ff.dtype == torch.float32 and torch.equal(feat2, feat)
+    assert rel_err(N(g_ff), N(r["grad_ff"])) <= 3e-5
+    assert rel_err(N(g_fvi), N(r["grad_fvi"])) <= 3e-5
+    # rasterize alone, tuple features
+    (a, b), idx3 = rasterize(H, W, t_fvz, t_fvi.detach(), [ff16[..., :2], ff16[..., 2:]], t_fnz >= 0.)
+    assert torch.equal(idx3, idx) and torch.equal(torch.cat([a, b], -1), feat)
+    with pytest.raises(RuntimeError):   # half is not a feature storage type
+        rasterize(H, W, t_fvz, t_fvi.detach(), ff16.to(torch.float16))
+
+
 def test_composition_equals_separate_calls():
     """test_dibr.py:482-529: dibr_rasterization == rasterize + dibr_soft_mask, torch.equal."""
     fvz, fvi, fnz = synthetic.icosphere_views(3, 3, seed=7)
