@@ -59,6 +59,9 @@ def parse():
     p.add_argument("--features", default="fp32", choices=["fp32", "bf16"],
                    help="storage of face_features / features / grad_features (arithmetic is fp32 either "
                         "way); BASELINE configs[3] names bf16, the reference itself only has fp32/fp64")
+    p.add_argument("--graph", action="store_true",
+                   help="N = 1: capture the resident forward+backward step in a CUDA graph and time replays "
+                        "(what launch-bound sizes such as c2 gain from it)")
     p.add_argument("--chunks", type=int, default=1,
                    help="N > 1: 1 = the all-gather of grad_face_features overlaps the soft-mask branch of "
                         "the backward (default); k > 1 = k view-chunks per step, chunk i's all-gather "
@@ -269,6 +272,24 @@ def run_ours(args):
             g_fvi, g_ff = chunked.finish()
         return g_fvi, g_ff
 
+    graph = None
+    if args.graph and world == 1:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            step_resident()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            graph_out = step_resident()
+        eager_step = step_resident
+
+        def step_resident(ev=None):     # noqa: F811 - replay; per-phase events do not exist inside a graph
+            if ev: ev[0].record()
+            graph.replay()
+            if ev: ev[1].record(); ev[2].record()
+            return graph_out
+
     for _ in range(args.warmup):
         step_resident()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3 * len(spans))] for _ in range(args.steps)]
@@ -448,7 +469,7 @@ def run_ours(args):
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "vertex_jitter": WORKLOADS[args.workload][5],
                    "views_per_gpu": B, "faces_per_view": F, "height": H,
-                   "width": W, "feat_dim": D, "features": args.features, "knum": KNUM, "sigmainv": SIGMAINV,
+                   "width": W, "feat_dim": D, "features": args.features, "cuda_graph": bool(args.graph and world == 1), "knum": KNUM, "sigmainv": SIGMAINV,
                    "boxlen": BOXLEN, "covered_fraction": covered,
                    "parallelism": (f"views sharded x{world}; NCCL all-gather of per-view grads, "
                                    + ("grad_face_features' gather overlapped with the soft-mask backward"

@@ -244,6 +244,48 @@ def test_bf16_feature_storage_vs_reference_cuda(D):
         rasterize(H, W, t_fvz, t_fvi.detach(), ff16.to(torch.float16))
 
 
+def test_forward_backward_capture_in_a_cuda_graph():
+    """The C ABI never synchronises, allocates or touches global state, so a whole
+    forward+backward step can be captured once and replayed (launch-bound sizes such as
+    BASELINE configs[1] spend most of a step on launch gaps otherwise)."""
+    from kaolin_b200.render.mesh import _host
+    fvz, fvi, fnz = synthetic.icosphere_views(4, 4, seed=17)
+    B, F = fvz.shape[:2]
+    H, W = 128, 128
+    ff = synthetic.random_features(B, F, 3, seed=2)
+    t_fvz, t_fvi, t_ff, t_fnz = T(fvz), T(fvi), T(ff), T(fnz)
+    gen = torch.Generator(device=DEV); gen.manual_seed(5)
+    g_feat = torch.rand((B, H, W, 3), device=DEV, generator=gen)
+    g_soft = torch.rand((B, H, W), device=DEV, generator=gen)
+
+    def step():
+        feat, idx, wts, soft, ws = _host.forward(3, H, W, t_fvz, t_fvi, t_ff, t_fnz, None, 1000., 1e-8,
+                                                 7000., 20., 30)
+        g_fvi, g_ff = _host.backward(H, W, g_feat, g_soft, idx, wts, soft, t_fvi, t_ff, 1000., 1e-8,
+                                     7000., 20., 30, ws, True)
+        return feat, idx, soft, g_fvi, g_ff
+
+    eager = [t.clone() for t in step()]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        step()                                   # warm-up on the capture stream
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        outs = step()
+    # new inputs through the same buffers: the replay must follow them
+    t_fvi.mul_(0.9); t_ff.add_(0.25)
+    graph.replay()
+    torch.cuda.synchronize()
+    replayed = [t.clone() for t in outs]
+    fresh = step()
+    assert torch.equal(replayed[1], fresh[1]) and torch.equal(replayed[0], fresh[0])
+    assert torch.equal(replayed[2], fresh[2])
+    assert rel_err(N(replayed[3]), N(fresh[3])) <= 1e-6 and rel_err(N(replayed[4]), N(fresh[4])) <= 1e-6
+    assert not torch.equal(eager[0], fresh[0])   # the inputs did change
+
+
 def test_composition_equals_separate_calls():
     """test_dibr.py:482-529: dibr_rasterization == rasterize + dibr_soft_mask, torch.equal."""
     fvz, fvi, fnz = synthetic.icosphere_views(3, 3, seed=7)
