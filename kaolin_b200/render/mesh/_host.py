@@ -51,9 +51,11 @@ def check_size(func, name, t, shape):
         raise RuntimeError(f"{func}: expected {name} of size {list(shape)}, got {list(t.shape)}")
 
 
-# fraction of the screen tiles whose soft-mask hits are cached for backward (the
-# silhouette band is a few percent of the image; tiles beyond the cache are recomputed)
-CACHE_TILE_FRACTION = 0.125
+# Screen tiles whose soft-mask hits are cached for backward: every tile if that fits in
+# CACHE_MAX_BYTES (small images: a third of the 16x16 tiles touch the silhouette at 256^2),
+# else as many as fit (1024^2 x 32 views: 28 % of the tiles, the silhouette needs 10 %).
+# Tiles beyond the cache are recomputed in backward: same results, several times slower.
+CACHE_TILE_FRACTION = 1.0
 CACHE_MIN_TILES = 64
 CACHE_MAX_BYTES = 4 << 30
 
