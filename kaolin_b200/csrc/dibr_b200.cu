@@ -1206,13 +1206,13 @@ __global__ void __launch_bounds__(kThreads, 4) soft_tiles_fwd_kernel(const __gri
 }
 
 // ---------------------------------------------------------------------------
-// Three-kernel soft-mask forward (knum <= 32, hit cache available):
+// Two-kernel soft-mask forward (knum <= 32, hit cache available):
 //   soft_enum_kernel : per silhouette tile, decides WHICH (pixel, face) pairs exist
 //                      (integer work only) and lays them out face-major in the tile's
 //                      cache block, with each pixel's slot list in face order;
-//   soft_eval_kernel : one thread per pair over all tiles — the expensive
-//                      distance / probability, dense and barrier-free;
-//   soft_fold_kernel : each pixel folds its probabilities in face order.
+//   soft_eval_kernel : one thread per pair - the expensive distance / probability,
+//                      dense - then each pixel folds its probabilities in face order
+//                      (a tile's pairs are all evaluated by the CTA that folds them).
 // Tiles that do not fit the cache go to fb_list and take the single-kernel path.
 constexpr int kEnumK = 32;
 
