@@ -156,9 +156,15 @@ def cpu_sample(workload, budget_s, threads=None):
     rng = np.random.default_rng(0)
     g_feat = rng.uniform(size=(1, H, W, D)).astype(np.float32)
     g_soft = rng.uniform(size=(1, H, W)).astype(np.float32)
-    if threads:
-        oracle.set_threads(threads)
-    cores = threads or oracle.max_threads()
+    if not threads:
+        # every CPU this process may run on - torchrun exports OMP_NUM_THREADS=1, which would
+        # otherwise silently make the N > 1 reference arm single-threaded
+        try:
+            threads = len(os.sched_getaffinity(0))
+        except AttributeError:
+            threads = os.cpu_count() or 1
+    oracle.set_threads(threads)
+    cores = threads
 
     def strips_for(nblocks, rows_per_block=4):
         nblocks = max(1, min(H // rows_per_block, nblocks))
