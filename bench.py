@@ -465,7 +465,7 @@ def run_ours(args):
     except Exception:
         traffic = None
     roofline = {
-        "kernel": "raster_bwd_kernel<3> (+2 output memsets) via dibr_b200_rasterize_backward — the "
+        "kernel": "raster_bwd_kernel<D> (+2 output memsets) via dibr_b200_backward with only grad_features — the "
                   "backward scatter BASELINE.json grades; the largest single kernel is "
                   "dibr_tile_fwd_kernel (see profiles/r1_kernels.md)",
         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
