@@ -514,6 +514,23 @@ def test_soft_mask_dense_overflow_path():
         assert rel_err(N(t_fvi.grad), o_g) <= 2e-5
 
 
+def test_dense_mesh_single_branch_calls():
+    """Aggregated binning (>= 32 faces per tile) with only one bin set in use: rasterize alone
+    and dibr_soft_mask alone on a dense mesh equal the fused call."""
+    fvz, fvi, fnz = synthetic.icosphere_views(1, 6, seed=5, jitter=0.0125)     # 81 920 faces
+    B, F = fvz.shape[:2]
+    H = W = 160                                                               # 100 tiles
+    ff = synthetic.random_features(B, F, 2, seed=4)
+    feat, soft, idx = dibr_rasterization(H, W, T(fvz), T(fvi), T(ff), T(fnz))
+    feat_r, idx_r = rasterize(H, W, T(fvz), T(fvi), T(ff), T(fnz) >= 0.)
+    soft_s = dibr_soft_mask(T(fvi), idx_r)
+    assert torch.equal(idx_r, idx) and torch.equal(feat_r, feat) and torch.equal(soft_s, soft)
+    assert 0.2 < (idx >= 0).float().mean().item() < 0.9
+    o_feat, o_soft, o_idx = oracle.dibr_rasterization(H, W, fvz, fvi, ff, fnz)
+    assert np.array_equal(N(idx), o_idx)
+    np.testing.assert_allclose(N(soft), o_soft, rtol=0, atol=1e-5)
+
+
 @pytest.mark.parametrize("cache_tiles", [0, 3, 10 ** 9])
 def test_soft_backward_cache_and_recompute_paths_agree(cache_tiles, monkeypatch):
     """The soft-mask backward streams over the hit cache filled by forward; tiles that
