@@ -60,11 +60,16 @@ CACHE_MIN_TILES = 64
 CACHE_MAX_BYTES = 4 << 30
 
 
+def cache_tiles_for(batch, height, width, knum):
+    """How many 16x16 tiles get a soft-mask hit-cache block (3072*knum + 17.4 KB each)."""
+    tiles = batch * ((height + 15) // 16) * ((width + 15) // 16)
+    want = max(CACHE_MIN_TILES, int(tiles * CACHE_TILE_FRACTION))
+    return min(tiles, want, max(1, CACHE_MAX_BYTES // (3072 * knum + 17500)))
+
+
 def workspace(batch, total_faces, height, width, device, knum=0):
     if knum > 0:
-        tiles = batch * ((height + 15) // 16) * ((width + 15) // 16)
-        want = max(CACHE_MIN_TILES, int(tiles * CACHE_TILE_FRACTION))
-        want = min(tiles, want, max(1, CACHE_MAX_BYTES // (3072 * knum + 17500)))
+        want = cache_tiles_for(batch, height, width, knum)
         n = _lib.lib().dibr_b200_workspace_bytes_cached(batch, total_faces, height, width, knum, want)
     else:
         n = _lib.lib().dibr_b200_workspace_bytes(batch, total_faces, height, width)

@@ -99,3 +99,19 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert "oracle/" not in src.replace("tests/", ""), f
+
+
+def test_hit_cache_sizing_policy():
+    """Every tile is cached when that fits in 4 GB (BASELINE configs[1]/[2]: a third of the tiles
+    touch the silhouette at 256^2 - caching 1/8 of them halved the throughput), else as many as fit."""
+    from kaolin_b200.render.mesh import _host
+    lib = _lib.lib()
+    assert _host.cache_tiles_for(8, 256, 256, 30) == 8 * 16 * 16                 # c2: all tiles
+    c3 = _host.cache_tiles_for(64, 512, 512, 30)
+    assert 0.5 * 64 * 1024 < c3 <= 64 * 1024                                      # c3: more than half
+    c4 = _host.cache_tiles_for(32, 1024, 1024, 30)
+    assert 0.25 * 32 * 4096 < c4 < 32 * 4096                                      # c4: the 4 GB cap
+    base = lib.dibr_b200_workspace_bytes(32, 32 * 20480, 1024, 1024)
+    full = lib.dibr_b200_workspace_bytes_cached(32, 32 * 20480, 1024, 1024, 30, c4)
+    assert base < full <= base + _host.CACHE_MAX_BYTES + (1 << 20)
+    assert _host.cache_tiles_for(1, 16, 16, 30) == 1
