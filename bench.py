@@ -55,6 +55,7 @@ def parse():
                    help="CPU work budget for the cpu_baseline sample")
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-ref-cuda", action="store_true")
+    p.add_argument("--no-e2e-images", action="store_true")
     p.add_argument("--ref-cuda-views", type=int, default=2)
     p.add_argument("--features", default="fp32", choices=["fp32", "bf16"],
                    help="storage of face_features / features / grad_features (arithmetic is fp32 either "
@@ -136,6 +137,33 @@ class ClockSampler:
                 "samples": len(sm)}
 
 
+def effective_cores():
+    """Host threads the CPU arm may really use: min(CPUs this process may run on, cgroup CPU
+    quota).  torchrun exports OMP_NUM_THREADS=1 (ignored on purpose); a container with a CFS
+    quota of q CPUs but 128 visible ones makes a 128-thread OpenMP team 10x SLOWER than q
+    threads (round 1: 0.016 vs 0.21 Mpx/s for the same commit), so the quota is honoured."""
+    try:
+        affinity = len(os.sched_getaffinity(0))
+    except AttributeError:
+        affinity = os.cpu_count() or 1
+    quota = None
+    try:
+        with open("/sys/fs/cgroup/cpu.max") as f:           # cgroup v2: "<quota|max> <period>"
+            q, per = f.read().split()
+            if q != "max":
+                quota = float(q) / float(per)
+    except Exception:
+        try:                                                  # cgroup v1
+            q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read())
+            per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+            if q > 0:
+                quota = q / per
+        except Exception:
+            quota = None
+    used = affinity if quota is None else max(1, min(affinity, int(quota + 0.5)))
+    return used, {"affinity": affinity, "cgroup_quota_cpus": quota, "used": used}
+
+
 def make_scene(workload, rank):
     from kaolin_b200 import synthetic
     B, level, H, W, D, jitter = WORKLOADS[workload]
@@ -157,12 +185,9 @@ def cpu_sample(workload, budget_s, threads=None):
     g_feat = rng.uniform(size=(1, H, W, D)).astype(np.float32)
     g_soft = rng.uniform(size=(1, H, W)).astype(np.float32)
     if not threads:
-        # every CPU this process may run on - torchrun exports OMP_NUM_THREADS=1, which would
-        # otherwise silently make the N > 1 reference arm single-threaded
-        try:
-            threads = len(os.sched_getaffinity(0))
-        except AttributeError:
-            threads = os.cpu_count() or 1
+        threads, cores_info = effective_cores()
+    else:
+        cores_info = {"used": threads}
     oracle.set_threads(threads)
     cores = threads
 
@@ -176,11 +201,20 @@ def cpu_sample(workload, budget_s, threads=None):
                          strips=probe)
     s.run()                                       # touch pages, start the OpenMP team
     t = time.perf_counter(); s.run(); dt = time.perf_counter() - t
+    # 1 thread vs the full team on the same 16 rows: a starved arm (quota, noisy neighbours) shows
+    # up as a speed-up far below the thread count
+    if threads > 1:
+        oracle.set_threads(1)
+        t = time.perf_counter(); s.run(); dt1 = time.perf_counter() - t
+        oracle.set_threads(threads)
+        cores_info = dict(cores_info, scaling_probe={"rows": 16, "threads_1_s": dt1, f"threads_{threads}_s": dt,
+                                                     "speedup": dt1 / max(dt, 1e-9)})
     nblocks = int(max(4, len(probe) * budget_s / max(dt, 1e-6)))
     strips = strips_for(nblocks)
     s = oracle.RowSample(H, W, fvz, fvi, ff, fnz, g_feat, g_soft, 0, 0, SIGMAINV, BOXLEN, KNUM, MULT, EPS,
                          strips=strips)
     rows = sum(b - a for a, b in strips)
+    cpu_sample.cores_info = cores_info
     return s, cores, (f"{rows} of {H} rows ({len(strips)} evenly spaced 4-row blocks) of 1 view of "
                       f"{workload} ({W}x{H}, {F} faces)")
 
@@ -210,7 +244,8 @@ def run_reference(args):
         "config": {"workload": args.workload, "vertex_jitter": WORKLOADS[args.workload][5],
                    "views_per_gpu": B, "faces_per_view": 20 * 4 ** level,
                    "height": H, "width": W, "feat_dim": D, "knum": KNUM, "sample": desc},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": desc,
+                         "cores_detail": getattr(cpu_sample, "cores_info", None)},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -233,7 +268,18 @@ def run_ours(args):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        # one box, NVLink only (north_star): no IB / socket transports; the collective kernels run
+        # on a HIGH-PRIORITY stream so that they get SM slots as soon as any CTA retires instead of
+        # queueing behind the (tens of thousands of CTAs of the) next kernels of the step
+        os.environ.setdefault("NCCL_P2P_LEVEL", "NVL")
+        os.environ.setdefault("NCCL_IB_DISABLE", "1")
+        os.environ.setdefault("NCCL_NET_DISABLE", "1")
+        opts = None
+        try:
+            opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+        except Exception:
+            opts = None
+        dist.init_process_group("nccl", device_id=dev, pg_options=opts)
     _lib.lib()
     if args.cache_fraction is not None:
         _host.CACHE_TILE_FRACTION = float(args.cache_fraction)
@@ -267,11 +313,12 @@ def run_ours(args):
             feat, idx, wts, soft, ws = _host.forward(mode, H, W, d_fvz[c0:c1], d_fvi[c0:c1], d_ff[c0:c1],
                                                      d_fnz[c0:c1], None, MULT, EPS, SIGMAINV, boxlen_m, KNUM)
             if ev: ev[3 * ci + 1].record()
-            bwd = lambda: _host.backward(H, W, g_feat[c0:c1], g_soft[c0:c1], idx, wts, soft, d_fvi[c0:c1],
-                                         d_ff[c0:c1], MULT, EPS, SIGMAINV, boxlen_m, KNUM, ws, True)
+            bwd = lambda hook=None: _host.backward(H, W, g_feat[c0:c1], g_soft[c0:c1], idx, wts, soft,
+                                                   d_fvi[c0:c1], d_ff[c0:c1], MULT, EPS, SIGMAINV, boxlen_m,
+                                                   KNUM, ws, True, feature_grad_hook=hook)
             if world > 1 and chunked is None:
-                with OverlappedGradAllGather(B * world) as gather:
-                    g_fvi, g_ff = bwd()
+                gather = OverlappedGradAllGather(B * world)
+                g_fvi, g_ff = bwd(gather.hook)
                 if ev: ev[3 * ci + 2].record()
                 g_fvi, g_ff = gather.finish(g_fvi)
             else:
@@ -306,22 +353,36 @@ def run_ours(args):
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3 * len(spans))] for _ in range(args.steps)]
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local)
+    # clocks are sampled on rank 0 only: 8 nvidia-smi pollers at 20 ms inside a 100 ms window
+    # were one suspect for round 1's slow N = 8 resident number
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local) \
+        if rank == 0 else None
     start.record()
     for k in range(args.steps):
         step_resident(evs[k])
     end.record()
     barrier()
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sampler is not None else None
     total_ms = start.elapsed_time(end)
+    # per-step device time on this rank (event at the start of step k -> start of step k+1)
+    marks = [e[0] for e in evs] + [end]
+    step_ms = [marks[k].elapsed_time(marks[k + 1]) for k in range(args.steps)]
     nch = len(spans)
     fwd_ms = statistics.mean(sum(e[3 * c].elapsed_time(e[3 * c + 1]) for c in range(nch)) for e in evs)
     bwd_ms = statistics.mean(sum(e[3 * c + 1].elapsed_time(e[3 * c + 2]) for c in range(nch)) for e in evs)
     t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+    per_rank = None
     if world > 1:
+        mine = torch.tensor([total_ms / args.steps, min(step_ms), statistics.median(step_ms), max(step_ms)],
+                            device=dev, dtype=torch.float64)
+        allr = torch.empty((world, 4), device=dev, dtype=torch.float64)
+        dist.all_gather_into_tensor(allr, mine)
+        per_rank = [[round(float(x), 4) for x in row] for row in allr.cpu()]
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = float(t.item()) / args.steps
     value = world * B * H * W / (ms_per_step * 1e-3) / 1e6
+    step_stats = {"min": min(step_ms), "median": statistics.median(step_ms), "max": max(step_ms),
+                  "rank": 0, "per_rank_mean_min_median_max": per_rank}
 
     # ---- the backward scatter kernel alone (roofline kernel) ---------------
     feat, idx, wts, soft, ws = _host.forward(mode, H, W, d_fvz, d_fvi, d_ff, d_fnz, None, MULT, EPS,
@@ -337,7 +398,24 @@ def run_ours(args):
         rb[2 * k + 1].record()
     torch.cuda.synchronize()
     raster_bwd_ms = statistics.mean(rb[2 * k].elapsed_time(rb[2 * k + 1]) for k in range(args.steps))
+    band_px = int(((idx < 0) & (soft > 0)).sum().item())     # uncovered pixels with a soft-mask value
     del feat, idx, wts, soft, ws
+
+    # ---- every kernel of the step, CUDA events around each launch (library trace) ----------
+    kernel_ms = {}
+    kernel_order = []
+    tsteps = max(3, min(10, args.steps))
+    for _ in range(tsteps):
+        _lib.trace_begin()
+        f_, i_, w_, s_, ws_ = _host.forward(mode, H, W, d_fvz, d_fvi, d_ff, d_fnz, None, MULT, EPS, SIGMAINV,
+                                            boxlen_m, KNUM)
+        _host.backward(H, W, g_feat, g_soft, i_, w_, s_, d_fvi, d_ff, MULT, EPS, SIGMAINV, boxlen_m, KNUM, ws_, True)
+        for name, ms in _lib.trace_end():
+            if name not in kernel_ms:
+                kernel_ms[name] = []
+                kernel_order.append(name)
+            kernel_ms[name].append(ms)
+        del f_, i_, w_, s_, ws_
 
     # ---- e2e: public API, host buffers, H2D + D2H inside the timed region --
     # Every step copies ITS inputs from pinned host memory and returns ITS gradients
@@ -381,8 +459,8 @@ def run_ours(args):
         elif len(spans) == 1:
             a_fvi.grad = None; a_ff.grad = None
             feat, soft, idx = dibr_rasterization(H, W, a_fvz, a_fvi, a_ff, a_fnz, SIGMAINV, BOXLEN, KNUM)
-            with OverlappedGradAllGather(B * world) as gather:
-                torch.autograd.backward([feat, soft], [g_feat, g_soft])
+            gather = OverlappedGradAllGather(B * world).attach(soft)
+            torch.autograd.backward([feat, soft], [g_feat, g_soft])
             full = gather.finish(a_fvi.grad, a_ff.grad)
             g1, g2 = full[0][rank * B:(rank + 1) * B], full[1][rank * B:(rank + 1) * B]
             loss = (soft.detach().sum() / soft.numel()).reshape(1)
@@ -448,6 +526,35 @@ def run_ours(args):
     h2d = sum(x.numel() * x.element_size() for x in (h_fvz, h_fvi, h_fnz, h_ff))
     d2h = sum(x.numel() * x.element_size() for x in host_out[0])
 
+    # ---- e2e_images (N = 1): as e2e, but the drop-in API's RETURN VALUES (features, soft_mask,
+    # face_idx) are downloaded as well - what a caller that post-processes the images on the
+    # host pays; PCIe-bound (28+ B per pixel)
+    e2e_images = None
+    if world == 1 and not args.no_e2e_images:
+        n_img = 3
+        h_img = (torch.empty((B, H, W, D), dtype=fdt).pin_memory(), torch.empty((B, H, W), dtype=torch.float32).pin_memory(),
+                 torch.empty((B, H, W), dtype=torch.int64).pin_memory())
+        def step_images():
+            a_fvz, a_fvi, a_ff, a_fnz = dev_in[0]
+            with torch.no_grad():
+                a_fvz.copy_(h_fvz, non_blocking=True); a_fvi.copy_(h_fvi, non_blocking=True)
+                a_ff.copy_(h_ff, non_blocking=True); a_fnz.copy_(h_fnz, non_blocking=True)
+            a_fvi.grad = None; a_ff.grad = None
+            feat, soft, idx = dibr_rasterization(H, W, a_fvz, a_fvi, a_ff, a_fnz, SIGMAINV, BOXLEN, KNUM)
+            torch.autograd.backward([feat, soft], [g_feat, g_soft])
+            h_img[0].copy_(feat.detach(), non_blocking=True); h_img[1].copy_(soft.detach(), non_blocking=True)
+            h_img[2].copy_(idx, non_blocking=True)
+            host_out[0][0].copy_(a_fvi.grad, non_blocking=True); host_out[0][1].copy_(a_ff.grad, non_blocking=True)
+        step_images(); torch.cuda.synchronize()
+        start.record()
+        for _ in range(n_img):
+            step_images()
+        end.record(); torch.cuda.synchronize()
+        ims = start.elapsed_time(end) / n_img
+        e2e_images = {"value": B * H * W / (ims * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": ims, "steps": n_img,
+                      "d2h_bytes_per_step": d2h + sum(x.numel() * x.element_size() for x in h_img)}
+        del h_img
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -457,21 +564,53 @@ def run_ours(args):
     A = algorithmic_bytes(B, F, H, W, D, s=2 if args.features == "bf16" else 4)
     ach = A["bwd_raster"] / (raster_bwd_ms * 1e-3) / 1e9
     traffic = None          # dram__bytes_read.sum + dram__bytes_write.sum of the same kernel (ncu --set full)
-    try:
-        prof = json.load(open(os.path.join(ROOT, "profiles", "r1_kernels.json")))
+    traffic_src = None
+    for prof_name in ("r2_kernels.json", "r1_kernels.json"):
+        try:
+            prof = json.load(open(os.path.join(ROOT, "profiles", prof_name)))
+        except Exception:
+            continue
+        want = "raster_bwd_rows_kernel" if "raster_bwd_rows_kernel" in kernel_ms else "raster_bwd_kernel"
         for name, e in prof.items():
-            if "raster_bwd_kernel" in name and args.workload == "c4_shard" and args.features == "fp32":
+            if want in name and args.workload == "c4_shard" and args.features == "fp32":
                 traffic = e.get("dram_traffic_bytes")
-    except Exception:
-        traffic = None
+                traffic_src = f"profiles/{prof_name} (ncu --set full, c4_shard)"
+        if traffic is not None:
+            break
+    # per-kernel table: CUDA-event time of every launch of one forward+backward (mean over the
+    # traced steps) and, where the kernel has compulsory traffic of its own (SURVEY.md §8d split by
+    # the kernel that moves it), algorithmic bytes -> GB/s -> fraction of the measured HBM peak
+    sF = 2 if args.features == "bf16" else 4
+    P_, NF_ = B * H * W, B * F
+    alg = {
+        "bin_faces_kernel<count>": NF_ * 28,                        # xy + validity
+        "bin_faces_kernel<fill>": NF_ * (28 + 2 * 16),              # + one bin entry per set
+        "dibr_tile_fwd_kernel": A["fwd"],                           # all per-pixel outputs + face reads
+        "raster_bwd_rows_kernel": P_ * (D * sF + 8 + 12) + NF_ * (24 + 3 * D * sF),
+        "raster_bwd_finalize_kernel": NF_ * (24 + 3 * D * 4),
+        "raster_bwd_kernel": A["bwd_raster"],
+        "soft_bwd_dense_kernel": band_px * 16 + NF_ * 24,           # soft, grad, idx of band pixels + grad_xy
+    }
+    total_kernel_ms = sum(statistics.mean(v) for v in kernel_ms.values()) or 1.0
+    kernels = []
+    for name in kernel_order:
+        ms = statistics.mean(kernel_ms[name])
+        row = {"kernel": name, "ms": round(ms, 4), "share_of_kernel_time": round(ms / total_kernel_ms, 4)}
+        if name in alg and ms > 0:
+            gbs = alg[name] / (ms * 1e-3) / 1e9
+            row.update({"algorithmic_bytes": int(alg[name]), "GBps": round(gbs, 1), "frac": round(gbs / peak, 4)})
+        kernels.append(row)
+    dominant = max(kernels, key=lambda r: r["ms"]) if kernels else None
     roofline = {
-        "kernel": "raster_bwd_kernel<D> (+2 output memsets) via dibr_b200_backward with only grad_features — the "
-                  "backward scatter BASELINE.json grades; the largest single kernel is "
-                  "dibr_tile_fwd_kernel (see profiles/r1_kernels.md)",
+        "kernel": "rasterize backward scatter (the kernel BASELINE.json grades): dibr_b200_backward with only "
+                  "grad_features = acc memset + raster_bwd_rows_kernel + raster_bwd_finalize_kernel "
+                  "(warp-reduction raster_bwd_kernel + 2 output memsets when the row-walk path does not apply)",
         "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-        "traffic": traffic, "traffic_source": "profiles/r1_kernels.json (ncu --set full, c4_shard)",
+        "traffic": traffic, "traffic_source": traffic_src,
         "peak_source": peak_src,
         "algorithmic_bytes_per_launch": A["bwd_raster"], "ms_per_launch": raster_bwd_ms,
+        "kernels": kernels, "kernels_traced_steps": tsteps,
+        "dominant_kernel": dominant,
         "phases": {
             "forward_ms": fwd_ms, "backward_ms": bwd_ms,
             "forward_GBps": A["fwd"] / (fwd_ms * 1e-3) / 1e9,
@@ -482,7 +621,7 @@ def run_ours(args):
     }
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "step_ms": step_stats, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.workload, "vertex_jitter": WORKLOADS[args.workload][5],
                    "views_per_gpu": B, "faces_per_view": F, "height": H,
@@ -499,8 +638,13 @@ def run_ours(args):
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "kaolin_b200.render.mesh.dibr_rasterization + autograd, pinned host buffers; "
                        "uploads/downloads double-buffered on side streams",
+                "d2h_contents": "the step's results as a training loop reads them: both gradients + the scalar "
+                                "loss; the rendered images (features, soft_mask, face_idx: 28+ B/px) stay on the "
+                                "device for the loss that consumes them - see e2e_images for the variant that "
+                                "downloads them too",
                 "host_wall_ms_per_step": wall_ms / args.steps},
-        "gpu_launches": 10 * len(spans) * args.steps,   # 6 forward + 4 backward kernels per (chunk of a) step
+        "e2e_images": e2e_images,
+        "gpu_launches": max(1, len(kernel_order)) * len(spans) * args.steps,   # kernels per (chunk of a) step, as traced
         "roofline": roofline,
         "triangle_pixel_tests_per_s": {
             "brute_force_equivalent": float(B) * H * W * F * 0.5 / (fwd_ms * 1e-3),
@@ -511,7 +655,8 @@ def run_ours(args):
         s, cores, desc = cpu_sample(args.workload, args.cpu_seconds)
         t0 = time.perf_counter(); s.run(); dt = time.perf_counter() - t0
         line["cpu_baseline"] = {"value": s.pixels / dt / 1e6, "unit": UNIT, "cores": cores,
-                                "kind": "port", "sample": desc, "seconds": dt}
+                                "kind": "port", "sample": desc, "seconds": dt,
+                                "cores_detail": getattr(cpu_sample, "cores_info", None)}
     else:
         line["cpu_baseline"] = None
 

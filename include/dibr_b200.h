@@ -47,6 +47,13 @@ typedef struct CUstream_st* dibr_b200_stream_t; /* == cudaStream_t */
 
 int dibr_b200_version(void);
 
+/* Diagnostics: per-kernel device time of every launch made by the CALLING THREAD between
+ * _begin and _end (thread-local: concurrent callers do not interact; no global state).
+ * _end synchronises the recorded events, writes up to `capacity` durations (ms, launch
+ * order) and the '\n'-separated kernel names, and returns the number of launches. */
+int dibr_b200_trace_begin(void);
+int dibr_b200_trace_end(char* names, size_t names_bytes, float* ms, int capacity);
+
 /* Scratch needed by any entry point for `batch` views with `total_faces` faces
  * in all views together on a height x width image. */
 size_t dibr_b200_workspace_bytes(int batch, int64_t total_faces, int height, int width);
@@ -100,6 +107,11 @@ int dibr_b200_forward(
  *                 zeroed first - lets a caller run the two branches as two calls (e.g. to
  *                 start sending grad_face_features while the soft-mask branch still runs);
  *                 grad_face_features is only touched when grad_features is given.
+ *  workspace      may be NULL when grad_soft_mask is NULL.  When it is at least
+ *                 dibr_b200_workspace_bytes() the rasterize branch (fp32 features, D <= 4,
+ *                 width a multiple of 8) runs the row-walk kernel, which scatters into padded
+ *                 per-face records in the workspace with 16-byte vector reductions; otherwise
+ *                 the warp-reduction kernel scatters straight into the outputs.
  */
 int dibr_b200_backward(
     int batch, int num_faces, int height, int width, int feat_dim,

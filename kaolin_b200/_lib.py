@@ -33,6 +33,8 @@ _sz = ctypes.c_size_t
 
 SIGNATURES = {
     "dibr_b200_version": (_i, []),
+    "dibr_b200_trace_begin": (_i, []),
+    "dibr_b200_trace_end": (_i, [ctypes.c_char_p, _sz, ctypes.POINTER(ctypes.c_float), _i]),
     "dibr_b200_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "dibr_b200_workspace_bytes_cached": (_sz, [_i, _i64, _i, _i, _i, _i64]),
     "dibr_b200_forward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _f, _f, _i,
@@ -92,6 +94,22 @@ def lib():
                 fn.argtypes = args
             _lib = handle
     return _lib
+
+
+def trace_begin():
+    """Per-kernel CUDA-event timing of every launch made by THIS thread until trace_end()."""
+    lib().dibr_b200_trace_begin()
+
+
+def trace_end(capacity=256):
+    """-> [(kernel name, milliseconds), ...] in launch order (synchronises the recorded events)."""
+    names = ctypes.create_string_buffer(64 * capacity)
+    ms = (ctypes.c_float * capacity)()
+    n = lib().dibr_b200_trace_end(names, len(names), ms, capacity)
+    if n < 0:
+        raise RuntimeError("dibr_b200_trace_end failed")
+    got = names.value.decode().split("\n")[:n]
+    return [(got[i], float(ms[i])) for i in range(min(n, capacity))]
 
 
 def check(status, what):

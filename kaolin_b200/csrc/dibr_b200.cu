@@ -27,6 +27,10 @@
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <type_traits>
+#include <vector>
+#include <string>
+#include <string.h>
+#include <stdlib.h>
 #include <stdint.h>
 
 #include "../../include/dibr_b200.h"
@@ -88,6 +92,40 @@ struct Scene {
 };
 
 __host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// ---------------------------------------------------------------------------
+// Per-kernel timing for bench.py's roofline table (dibr_b200_trace_begin/_end):
+// THREAD-LOCAL state, so the library stays re-entrant; when a trace is open on the
+// calling thread every kernel launch is bracketed by a pair of CUDA events on the
+// launch stream.  Off (the default) it costs one thread-local load per launch.
+struct TraceState {
+  bool on = false;
+  int used = 0;
+  std::vector<cudaEvent_t> pool;
+  std::vector<const char*> names;
+};
+thread_local TraceState g_trace;
+
+struct Span {
+  cudaStream_t st;
+  bool on;
+  Span(const char* name, cudaStream_t st_) : st(st_), on(g_trace.on) {
+    if (!on) return;
+    TraceState& t = g_trace;
+    while ((int)t.pool.size() < t.used + 2) {
+      cudaEvent_t e;
+      if (cudaEventCreate(&e) != cudaSuccess) { on = false; return; }
+      t.pool.push_back(e);
+    }
+    t.names.push_back(name);
+    cudaEventRecord(t.pool[t.used], st);
+  }
+  ~Span() {
+    if (!on) return;
+    cudaEventRecord(g_trace.pool[g_trace.used + 1], st);
+    g_trace.used += 2;
+  }
+};
 
 // ---------------------------------------------------------------------------
 // PTX helpers: mbarrier + 1-D bulk TMA (global -> shared).
@@ -1606,6 +1644,247 @@ __global__ void __launch_bounds__(kThreads, 6) raster_bwd_kernel(const __grid_co
 }
 
 // ---------------------------------------------------------------------------
+// Rasterize backward, ROW-WALK variant (the one the fused path uses when the feature
+// dim is 1..4 fp32 and the image width a multiple of 8).
+//
+// Measured on B200 (scripts/microbench.cu): SHFL issues at 1 warp-instruction per
+// clock per SM (a quarter of the FFMA rate), and a vector reduction RED.E.ADD.F32x4
+// costs the same per lane as a scalar one (228 G lane-ops/s chip-wide).  The kernel
+// above spends 75 shuffles per covered warp on its segmented reduction and 12 scalar /
+// v2 reductions per (warp, face) group; this one uses neither:
+//   * a warp owns 32 image rows x `strip` columns; LANE = ROW.  The lane walks along its
+//     row and accumulates the 6 + 3*D partial sums of the current face in REGISTERS; when
+//     face_idx changes it flushes them with (6+3D+3)/4 vector reductions into a padded
+//     per-face accumulator (acc[face][16] for D = 3: 64-byte records, 16-byte aligned) and
+//     reloads the face constants.  No shuffles, no match, no leader election;
+//   * the pixel streams (face_idx 8 B, weights 12 B, upstream gradient 4*D B per pixel) are
+//     staged per 8-column slab with 16-byte cp.async (LDGSTS) into rows padded to an odd
+//     number of 16-byte chunks, double buffered, and read back with LDS.128 (conflict free:
+//     8 consecutive rows cover the 32 banks);
+//   * raster_bwd_finalize_kernel unpacks acc into grad_face_vertices_image /
+//     grad_face_features (which therefore need no memset).
+// Per-pixel arithmetic is the reference's operation tree (dibr_math.cuh,
+// raster_backward_geom / _feature) with the face-constant factors hoisted; the only
+// change is g * (1 / k3^2) for g / k3^2 (<= 1 ulp per term).
+constexpr int kRwSlab = 8;   // columns per staged slab
+
+template <int DT>
+struct RwCfg {
+  static constexpr int kIdxPitch = 80;                          // 8 px * 8 B = 64 -> 5 chunks
+  static constexpr int kWPitch = 112;                           // 8 px * 12 B = 96 -> 7 chunks
+  static constexpr int kGRow = kRwSlab * DT * 4;
+  static constexpr int kGPitch = ((kGRow / 16) & 1) ? kGRow : kGRow + 16;
+  static constexpr int kStage = 32 * (kIdxPitch + kWPitch + kGPitch);
+  static constexpr int kVals = 6 + 3 * DT;
+  static constexpr int kAcc = (kVals + 3) & ~3;                 // floats per face record
+};
+constexpr int kAccMax = 20;  // D = 4
+
+__device__ __forceinline__ void cp_async16(void* dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+struct RowBwdArgs {
+  int B, H, W, F, strip, jobs_x, jobs_y;
+  const float* grad_feat; const int64_t* idx; const float* w; const float* xy; const float* feat;
+  float eps;
+  float* acc;  // [B*F][RwCfg<D>::kAcc], zeroed
+};
+
+template <int DT>
+struct RowFace {          // constants of the face a lane is currently accumulating
+  float ax, ay, bx, by, cx, cy;
+  float pp, n, m, q, k3, rk;
+  float qk3, nk3n, ppk3n, mk3;  // q*k3, -(n*k3), -(pp*k3), m*k3  (dw1ds, dw1dt, dw2ds, dw2dt)
+  float d1[DT], d2[DT];
+};
+
+template <int DT>
+__device__ __forceinline__ void row_face_load(const RowBwdArgs& a, int64_t face, RowFace<DT>& c) {
+  const float2* pp = reinterpret_cast<const float2*>(a.xy + face * 6);
+  const float2 pa = __ldg(pp), pb = __ldg(pp + 1), pc = __ldg(pp + 2);
+  const float* cf = a.feat + face * 3 * DT;
+  float c0[DT], c1[DT], c2[DT];
+#pragma unroll
+  for (int d = 0; d < DT; ++d) { c0[d] = __ldg(cf + d); c1[d] = __ldg(cf + DT + d); c2[d] = __ldg(cf + 2 * DT + d); }
+  c.ax = pa.x; c.ay = pa.y; c.bx = pb.x; c.by = pb.y; c.cx = pc.x; c.cy = pc.y;
+  c.pp = fsub(c.by, c.ay); c.n = fsub(c.cx, c.ax); c.m = fsub(c.bx, c.ax); c.q = fsub(c.cy, c.ay);
+  float k3 = ffma(c.m, c.q, -fmul(c.pp, c.n));
+  {
+    const double e = (f2u(k3) >> 31) ? -fabs((double)a.eps) : fabs((double)a.eps);
+    k3 = d2f(dibr::dadd((double)k3, e));
+  }
+  c.k3 = k3;
+  c.rk = fdiv(1.0f, fmul(k3, k3));
+  c.qk3 = fmul(c.q, k3); c.nk3n = -fmul(c.n, k3); c.ppk3n = -fmul(c.pp, k3); c.mk3 = fmul(c.m, k3);
+#pragma unroll
+  for (int d = 0; d < DT; ++d) { c.d1[d] = fsub(c1[d], c0[d]); c.d2[d] = fsub(c2[d], c0[d]); }
+}
+
+template <int DT>
+__device__ __forceinline__ void row_pixel(const RowFace<DT>& c, float aw, float bw, float cw, const float* g,
+                                          float (&acc)[RwCfg<DT>::kAcc]) {
+  const float y0 = ffma(c.cy, cw, ffma(c.ay, aw, fmul(c.by, bw)));
+  const float x0 = ffma(c.cx, cw, ffma(c.ax, aw, fmul(c.bx, bw)));
+  const float t = fsub(y0, c.ay), s = fsub(x0, c.ax);
+  const float k1 = ffma(c.q, s, -fmul(c.n, t));
+  const float k2 = ffma(c.m, t, -fmul(c.pp, s));
+  const float tk3 = fmul(t, c.k3), sk3 = fmul(s, c.k3);
+  const float dw1dm = -fmul(c.q, k1);
+  const float dw2dm = ffma(-c.q, k2, tk3);
+  const float dw1dn = ffma(c.pp, k1, -tk3);
+  const float dw1dp = fmul(c.n, k1);
+  const float dw1dq = ffma(-c.m, k1, sk3);
+  const float dw2dp = ffma(c.n, k2, -sk3);
+  const float dw2dn = fmul(c.pp, k2);
+  const float dw2dq = -fmul(c.m, k2);
+  const float n1ay = fadd(c.nk3n, fadd(dw1dp, dw1dq));
+  const float n1ax = fadd(c.qk3, fadd(dw1dm, dw1dn));
+  const float n2ax = fadd(c.ppk3n, fadd(dw2dm, dw2dn));
+  const float n2ay = fadd(c.mk3, fadd(dw2dp, dw2dq));
+#pragma unroll
+  for (int d = 0; d < DT; ++d) {
+    const float dl = fmul(g[d], c.rk);
+    const float d1 = c.d1[d], d2 = c.d2[d];
+    acc[0] = ffma(ffma(-n2ax, d2, -fmul(n1ax, d1)), dl, acc[0]);
+    acc[1] = ffma(ffma(-n2ay, d2, -fmul(n1ay, d1)), dl, acc[1]);
+    acc[2] = ffma(ffma(dw1dm, d1, fmul(dw2dm, d2)), dl, acc[2]);
+    acc[3] = ffma(ffma(dw1dp, d1, fmul(dw2dp, d2)), dl, acc[3]);
+    acc[4] = ffma(ffma(dw1dn, d1, fmul(dw2dn, d2)), dl, acc[4]);
+    acc[5] = ffma(ffma(dw1dq, d1, fmul(dw2dq, d2)), dl, acc[5]);
+    acc[6 + d] = ffma(g[d], aw, acc[6 + d]);
+    acc[6 + DT + d] = ffma(g[d], bw, acc[6 + DT + d]);
+    acc[6 + 2 * DT + d] = ffma(g[d], cw, acc[6 + 2 * DT + d]);
+  }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(32) raster_bwd_rows_kernel(const __grid_constant__ RowBwdArgs a) {
+  using C = RwCfg<DT>;
+  __shared__ __align__(128) unsigned char smem[2 * C::kStage];
+  const int lane = threadIdx.x;
+  int job = blockIdx.x;
+  const int jx = job % a.jobs_x; job /= a.jobs_x;
+  const int jy = job % a.jobs_y;
+  const int b = job / a.jobs_y;
+  const int row0 = jy * 32, col0 = jx * a.strip;
+  const int col1 = min(a.W, col0 + a.strip);
+  const int nslabs = (col1 - col0) / kRwSlab;
+  const bool row_ok = row0 + lane < a.H;
+  const int64_t pix0 = ((int64_t)b * a.H + row0) * a.W;  // first pixel of the job's first row
+  const int64_t fbase = (int64_t)b * a.F;
+
+  auto issue = [&](int s, int buf) {
+    unsigned char* base = smem + buf * C::kStage;
+    const int x = col0 + s * kRwSlab;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {           // face_idx: 4 chunks per row
+      const int r = (lane >> 2) + 8 * j, ch = lane & 3;
+      if (row0 + r < a.H)
+        cp_async16(base + r * C::kIdxPitch + ch * 16,
+                   reinterpret_cast<const char*>(a.idx + pix0 + (int64_t)r * a.W + x) + ch * 16);
+    }
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {           // weights: 6 chunks per row
+      const int k = lane + 32 * j, r = k / 6, ch = k - r * 6;
+      if (row0 + r < a.H)
+        cp_async16(base + 32 * C::kIdxPitch + r * C::kWPitch + ch * 16,
+                   reinterpret_cast<const char*>(a.w + (pix0 + (int64_t)r * a.W + x) * 3) + ch * 16);
+    }
+    constexpr int GC = C::kGRow / 16;       // upstream gradient: 2*D chunks per row
+#pragma unroll
+    for (int j = 0; j < GC; ++j) {
+      const int k = lane + 32 * j, r = k / GC, ch = k - r * GC;
+      if (row0 + r < a.H)
+        cp_async16(base + 32 * (C::kIdxPitch + C::kWPitch) + r * C::kGPitch + ch * 16,
+                   reinterpret_cast<const char*>(a.grad_feat + (pix0 + (int64_t)r * a.W + x) * DT) + ch * 16);
+    }
+    cp_async_commit();
+  };
+
+  int cur = -1;
+  RowFace<DT> fc;
+  float acc[C::kAcc];
+#pragma unroll
+  for (int i = 0; i < C::kAcc; ++i) acc[i] = 0.f;
+
+  auto flush = [&]() {
+    float4* p = reinterpret_cast<float4*>(a.acc + (fbase + cur) * C::kAcc);
+#pragma unroll
+    for (int i = 0; i < C::kAcc; i += 4) atomicAdd(p + (i >> 2), make_float4(acc[i], acc[i + 1], acc[i + 2], acc[i + 3]));
+  };
+
+  if (nslabs > 0) issue(0, 0);
+  for (int s = 0; s < nslabs; ++s) {
+    if (s + 1 < nslabs) { issue(s + 1, (s + 1) & 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+    __syncwarp();
+    const unsigned char* base = smem + (s & 1) * C::kStage;
+    if (row_ok) {
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(base + lane * C::kIdxPitch + half * 32);
+        const ulonglong2 i01 = ip[0], i23 = ip[1];
+        int f[4] = {(int)(long long)i01.x, (int)(long long)i01.y, (int)(long long)i23.x, (int)(long long)i23.y};
+        bool any = cur >= 0;
+#pragma unroll
+        for (int p = 0; p < 4; ++p) { f[p] = f[p] < 0 ? -1 : f[p]; any = any || f[p] >= 0; }
+        if (!any) continue;
+        const float4* wp = reinterpret_cast<const float4*>(base + 32 * C::kIdxPitch + lane * C::kWPitch + half * 48);
+        const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2];
+        const float wv[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
+        const float4* gp = reinterpret_cast<const float4*>(base + 32 * (C::kIdxPitch + C::kWPitch) + lane * C::kGPitch + half * (16 * DT));
+        float gv[4 * DT];
+#pragma unroll
+        for (int k = 0; k < DT; ++k) { const float4 t = gp[k]; gv[4 * k] = t.x; gv[4 * k + 1] = t.y; gv[4 * k + 2] = t.z; gv[4 * k + 3] = t.w; }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          if (f[p] != cur) {
+            if (cur >= 0) flush();
+            cur = f[p];
+            if (cur >= 0) {
+              row_face_load<DT>(a, fbase + cur, fc);
+#pragma unroll
+              for (int i = 0; i < C::kAcc; ++i) acc[i] = 0.f;
+            }
+          }
+          if (cur >= 0) row_pixel<DT>(fc, wv[3 * p], wv[3 * p + 1], wv[3 * p + 2], &gv[DT * p], acc);
+        }
+      }
+    }
+    __syncwarp();  // everyone is done with this buffer before slab s+2 lands in it
+  }
+  if (cur >= 0) flush();
+}
+
+// acc[face][kAcc] -> grad_face_vertices_image (NF,3,2) (= or +=) and grad_face_features (NF,3,D) (=).
+template <int DT>
+__global__ void __launch_bounds__(256) raster_bwd_finalize_kernel(const float* __restrict__ acc, int64_t NF,
+                                                                 float* __restrict__ g_xy, float* __restrict__ g_ff,
+                                                                 int accumulate_xy) {
+  using C = RwCfg<DT>;
+  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= NF) return;
+  float v[C::kAcc];
+  const float4* p = reinterpret_cast<const float4*>(acc + f * C::kAcc);
+#pragma unroll
+  for (int i = 0; i < C::kAcc; i += 4) { const float4 t = __ldcs(p + (i >> 2)); v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w; }
+  float2* gx = reinterpret_cast<float2*>(g_xy + f * 6);
+  if (accumulate_xy) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) { const float2 o = gx[j]; gx[j] = make_float2(o.x + v[2 * j], o.y + v[2 * j + 1]); }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) gx[j] = make_float2(v[2 * j], v[2 * j + 1]);
+  }
+  float* gf = g_ff + f * 3 * DT;
+#pragma unroll
+  for (int j = 0; j < 3 * DT; ++j) gf[j] = v[6 + j];
+}
+
+// ---------------------------------------------------------------------------
 // Soft-mask backward from stored K-lists (operator contract, dibr_soft_mask_cuda.cu:230-353).
 struct SoftBwdListArgs {
   int B, H, W, F, K;
@@ -1661,8 +1940,9 @@ int bins_per_view(int H, int W) {
 
 // Workspace layout (all pieces 256-byte aligned):
 //   cnt [2*B*NB] int + pool_ctr + fb_ctr + band_ctr | off [2*B*NB] int | fb_list, band_list [tiles] int |
-//   entries [2*4*NF] int4 | pool_hdr [pool_tiles] int4 | pool_data [pool_tiles][3][256*K] u32
-struct Layout { size_t cnt, off, mode, ent, base; };
+//   entries [2*4*NF] int4 | acc [NF][<=20] f32 (rasterize backward) | pool_hdr [pool_tiles] int4 |
+//   pool_data [pool_tiles][3][256*K] u32
+struct Layout { size_t cnt, off, mode, ent, acc, base; };
 
 Layout layout_for(int B, int64_t NF, int H, int W) {
   Layout L;
@@ -1671,7 +1951,8 @@ Layout layout_for(int B, int64_t NF, int H, int W) {
   L.off = align_up((size_t)2 * B * bins_per_view(H, W) * sizeof(int), 256);
   L.mode = align_up(tiles * sizeof(int), 256) + align_up(tiles * kBandRec * sizeof(int), 256);
   L.ent = align_up((size_t)2 * 4 * (size_t)(NF > 0 ? NF : 1) * sizeof(int4), 256);
-  L.base = L.cnt + L.off + L.mode + L.ent + 256;
+  L.acc = align_up((size_t)(NF > 0 ? NF : 1) * kAccMax * sizeof(float), 256);  // rasterize-backward face records
+  L.base = L.cnt + L.off + L.mode + L.ent + L.acc + 256;
   return L;
 }
 
@@ -1697,7 +1978,7 @@ int setup_scene(Scene& s, int B, int64_t NF, int F, int H, int W, float multipli
   const Layout Lo = layout_for(B, NF, H, W);
   char* p = (char*)align_up((size_t)ws, 256);
   char* const end = (char*)ws + ws_bytes;
-  if (ws_bytes < Lo.base || p + Lo.cnt + Lo.off + Lo.mode + Lo.ent > end) return DIBR_B200_EWORKSPACE;
+  if (ws_bytes < Lo.base || p + Lo.cnt + Lo.off + Lo.mode + Lo.ent + Lo.acc > end) return DIBR_B200_EWORKSPACE;
   s.B = B; s.H = H; s.W = W; s.F = F; s.NF = NF;
   s.multiplier = multiplier; s.margin = margin;
   s.grid = make_grid(multiplier, W, H);
@@ -1724,6 +2005,7 @@ int setup_scene(Scene& s, int B, int64_t NF, int F, int H, int W, float multipli
   s.band_list = (int*)(p + align_up((size_t)s.ntx[0] * s.nty[0] * B * sizeof(int), 256));
   p += Lo.mode;
   s.entries = (int4*)p; p += Lo.ent;
+  p += Lo.acc;
   s.pool_tiles = 0; s.pool_K = knum > 0 ? knum : 1; s.pool_hdr = nullptr; s.pool_data = nullptr;
   s.pool_na = nullptr; s.pool_aux = nullptr; s.pool_slots = nullptr;
   if (knum > 0) {
@@ -1763,11 +2045,20 @@ int build_bins(const Scene& s, int sets, cudaStream_t st) {
     const int threads = agg ? kBinThreadsAgg : kBinThreadsPlain;
     const unsigned blocks = (unsigned)((s.NF + threads - 1) / threads);
     // dense meshes (tens of faces per 16x16 tile) hammer a few counters: aggregate per CTA
-    if (agg) bin_faces_kernel<false, true><<<blocks, threads, 0, st>>>(s, sets);
-    else bin_faces_kernel<false, false><<<blocks, threads, 0, st>>>(s, sets);
-    scan_bins_kernel<<<2 * s.B, 1024, 0, st>>>(s);
-    if (agg) bin_faces_kernel<true, true><<<blocks, threads, 0, st>>>(s, sets);
-    else bin_faces_kernel<true, false><<<blocks, threads, 0, st>>>(s, sets);
+    {
+      Span sp("bin_faces_kernel<count>", st);
+      if (agg) bin_faces_kernel<false, true><<<blocks, threads, 0, st>>>(s, sets);
+      else bin_faces_kernel<false, false><<<blocks, threads, 0, st>>>(s, sets);
+    }
+    {
+      Span sp("scan_bins_kernel", st);
+      scan_bins_kernel<<<2 * s.B, 1024, 0, st>>>(s);
+    }
+    {
+      Span sp("bin_faces_kernel<fill>", st);
+      if (agg) bin_faces_kernel<true, true><<<blocks, threads, 0, st>>>(s, sets);
+      else bin_faces_kernel<true, false><<<blocks, threads, 0, st>>>(s, sets);
+    }
   }
   return (int)cudaGetLastError();
 }
@@ -1793,19 +2084,30 @@ template <bool R, bool S, bool K, typename FT = float>
 void launch_fwd(const FwdArgs& a0, cudaStream_t st) {
   FwdArgs a = a0;
   a.from_fb = 0;
-  dibr_tile_fwd_kernel<R, S, K, FT><<<tile_grid(a.s), kThreads, 0, st>>>(a);
+  {
+    Span sp("dibr_tile_fwd_kernel", st);
+    dibr_tile_fwd_kernel<R, S, K, FT><<<tile_grid(a.s), kThreads, 0, st>>>(a);
+  }
   if (S) {
     cudaFuncSetAttribute(soft_tiles_fwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)sizeof(SoftSmem));
     const unsigned g1 = persistent_grid(a.s, soft_tiles_fwd_kernel<K>, sizeof(SoftSmem));
     if (!K && a.cache && a.s.pool_tiles > 0 && a.s.pool_slots != nullptr) {
       // enumerate -> evaluate densely -> fold; tiles beyond the cache take the single-kernel path
-      soft_enum_kernel<<<persistent_grid(a.s, soft_enum_kernel), kThreads, 0, st>>>(a);
-      soft_eval_kernel<<<(unsigned)a.s.pool_tiles, kThreads, 0, st>>>(a);
+      {
+        Span sp("soft_enum_kernel", st);
+        soft_enum_kernel<<<persistent_grid(a.s, soft_enum_kernel), kThreads, 0, st>>>(a);
+      }
+      {
+        Span sp("soft_eval_kernel", st);
+        soft_eval_kernel<<<(unsigned)a.s.pool_tiles, kThreads, 0, st>>>(a);
+      }
       a.from_fb = 1;
       a.cache = 0;
+      Span sp("soft_tiles_fwd_kernel<leftovers>", st);
       soft_tiles_fwd_kernel<K><<<g1, kThreads, sizeof(SoftSmem), st>>>(a);
     } else {
+      Span sp("soft_tiles_fwd_kernel", st);
       soft_tiles_fwd_kernel<K><<<g1, kThreads, sizeof(SoftSmem), st>>>(a);
     }
   }
@@ -1814,6 +2116,7 @@ void launch_fwd(const FwdArgs& a0, cudaStream_t st) {
 template <typename FT>
 int launch_raster_bwd(const RasterBwdArgs& a, cudaStream_t st) {
   const dim3 grid((unsigned)a.ntx, (unsigned)a.nty, (unsigned)a.B);
+  Span sp("raster_bwd_kernel", st);
   switch (a.D) {
     case 1: raster_bwd_kernel<1, FT><<<grid, kThreads, 0, st>>>(a); break;
     case 2: raster_bwd_kernel<2, FT><<<grid, kThreads, 0, st>>>(a); break;
@@ -1824,12 +2127,88 @@ int launch_raster_bwd(const RasterBwdArgs& a, cudaStream_t st) {
   return (int)cudaGetLastError();
 }
 
+// The face-record region of a workspace (nullptr: none / too small -> warp-reduction kernel).
+float* acc_region(void* ws, size_t ws_bytes, int B, int64_t NF, int H, int W) {
+  if (!ws) return nullptr;
+  const Layout Lo = layout_for(B, NF, H, W);
+  char* p = (char*)align_up((size_t)ws, 256);
+  if (ws_bytes < Lo.base || p + Lo.cnt + Lo.off + Lo.mode + Lo.ent + Lo.acc > (char*)ws + ws_bytes) return nullptr;
+  return (float*)(p + Lo.cnt + Lo.off + Lo.mode + Lo.ent);
+}
+
+template <int DT>
+int launch_rows_t(const RowBwdArgs& a, int64_t NF, float* g_xy, float* g_ff, int accumulate_xy, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(a.acc, 0, (size_t)NF * RwCfg<DT>::kAcc * sizeof(float), st);
+  if (e != cudaSuccess) return (int)e;
+  {
+    Span sp("raster_bwd_rows_kernel", st);
+    raster_bwd_rows_kernel<DT><<<(unsigned)(a.jobs_x * a.jobs_y * a.B), 32, 0, st>>>(a);
+  }
+  {
+    Span sp("raster_bwd_finalize_kernel", st);
+    raster_bwd_finalize_kernel<DT><<<(unsigned)((NF + 255) / 256), 256, 0, st>>>(a.acc, NF, g_xy, g_ff, accumulate_xy);
+  }
+  return (int)cudaGetLastError();
+}
+
+// Row-walk rasterize backward: one warp per 32 rows x strip columns; the strip is as long as
+// still leaves a few waves of single-warp CTAs (longer strips = fewer cut face runs).
+int launch_raster_bwd_rows(const RasterBwdArgs& r, float* acc, int accumulate_xy, cudaStream_t st) {
+  RowBwdArgs a;
+  a.B = r.B; a.H = r.H; a.W = r.W; a.F = r.F;
+  a.grad_feat = static_cast<const float*>(r.grad_feat); a.idx = r.idx; a.w = r.w; a.xy = r.xy;
+  a.feat = static_cast<const float*>(r.feat); a.eps = r.eps; a.acc = acc;
+  a.jobs_y = (r.H + 31) / 32;
+  int strip = 128;
+  while (strip > kRwSlab && (int64_t)r.B * a.jobs_y * ((r.W + strip - 1) / strip) < 8192) strip >>= 1;
+  a.strip = strip;
+  a.jobs_x = (r.W + strip - 1) / strip;
+  const int64_t NF = (int64_t)r.B * r.F;
+  switch (r.D) {
+    case 1: return launch_rows_t<1>(a, NF, r.grad_xy, r.grad_feat_out, accumulate_xy, st);
+    case 2: return launch_rows_t<2>(a, NF, r.grad_xy, r.grad_feat_out, accumulate_xy, st);
+    case 3: return launch_rows_t<3>(a, NF, r.grad_xy, r.grad_feat_out, accumulate_xy, st);
+    case 4: return launch_rows_t<4>(a, NF, r.grad_xy, r.grad_feat_out, accumulate_xy, st);
+    default: return DIBR_B200_EINVAL;
+  }
+}
+
 }  // namespace
 
 // ===========================================================================
 extern "C" {
 
-int dibr_b200_version(void) { return 100; }
+int dibr_b200_trace_begin(void) {
+  g_trace.on = true;
+  g_trace.used = 0;
+  g_trace.names.clear();
+  return 0;
+}
+
+int dibr_b200_trace_end(char* names, size_t names_bytes, float* ms, int capacity) {
+  TraceState& t = g_trace;
+  t.on = false;
+  const int n = t.used / 2;
+  std::string joined;
+  for (int i = 0; i < n; ++i) {
+    if (cudaEventSynchronize(t.pool[2 * i + 1]) != cudaSuccess) return DIBR_B200_EINVAL;
+    float v = 0.f;
+    if (cudaEventElapsedTime(&v, t.pool[2 * i], t.pool[2 * i + 1]) != cudaSuccess) return DIBR_B200_EINVAL;
+    if (ms && i < capacity) ms[i] = v;
+    joined += t.names[i];
+    joined += '\n';
+  }
+  if (names && names_bytes > 0) {
+    const size_t c = joined.size() < names_bytes - 1 ? joined.size() : names_bytes - 1;
+    memcpy(names, joined.data(), c);
+    names[c] = 0;
+  }
+  t.used = 0;
+  t.names.clear();
+  return n;
+}
+
+int dibr_b200_version(void) { return 200; }
 
 size_t dibr_b200_workspace_bytes(int batch, int64_t total_faces, int height, int width) {
   if (check_dims(batch, total_faces, height, width)) return 0;
@@ -1925,16 +2304,23 @@ static int backward_impl(int batch, int num_faces, int height, int width, int fe
   if (num_faces > 0 && !face_vertices_image) return DIBR_B200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
-  if (!(flags & DIBR_B200_ACCUMULATE)) {
+  const bool run_raster = grad_features && feat_dim > 0;
+  // row-walk kernel: fp32 features, D <= 4, rows a multiple of 8 px, a workspace with the face records
+  float* acc = nullptr;
+  if (run_raster && !bf16 && feat_dim <= 4 && (width % kRwSlab) == 0 && NF > 0) {
+    const char* force = getenv("DIBR_B200_RASTER_BWD");   // "warp": A/B against the warp-reduction kernel
+    if (!(force && force[0] == 'w')) acc = acc_region(workspace, workspace_bytes_, batch, NF, height, width);
+  }
+  if (!(flags & DIBR_B200_ACCUMULATE) && !acc) {
     e = cudaMemsetAsync(grad_face_vertices_image, 0, (size_t)NF * 6 * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
   }
-  if (grad_face_features && feat_dim > 0 && (grad_features || !(flags & DIBR_B200_ACCUMULATE))) {
+  if (grad_face_features && feat_dim > 0 && (grad_features || !(flags & DIBR_B200_ACCUMULATE)) && !acc) {
     e = cudaMemsetAsync(grad_face_features, 0, (size_t)NF * 3 * feat_dim * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
   }
   if (NF == 0) return 0;
-  if (grad_features && feat_dim > 0) {
+  if (run_raster) {
     if (!output_weights || !face_features || !grad_face_features) return DIBR_B200_EINVAL;
     RasterBwdArgs a;
     a.B = batch; a.H = height; a.W = width; a.F = num_faces; a.D = feat_dim;
@@ -1942,7 +2328,8 @@ static int backward_impl(int batch, int num_faces, int height, int width, int fe
     a.grad_feat = grad_features; a.idx = face_idx; a.w = output_weights; a.xy = face_vertices_image;
     a.feat = face_features; a.eps = eps; a.grad_xy = grad_face_vertices_image;
     a.grad_feat_out = grad_face_features;
-    rc = bf16 ? launch_raster_bwd<__nv_bfloat16>(a, st) : launch_raster_bwd<float>(a, st);
+    if (acc) rc = launch_raster_bwd_rows(a, acc, (flags & DIBR_B200_ACCUMULATE) ? 1 : 0, st);
+    else rc = bf16 ? launch_raster_bwd<__nv_bfloat16>(a, st) : launch_raster_bwd<float>(a, st);
     if (rc) return rc;
   }
   if (grad_soft_mask) {
@@ -1962,11 +2349,16 @@ static int backward_impl(int batch, int num_faces, int height, int width, int fe
       rc = build_bins(s, 2, st);
       if (rc) return rc;
       a.from_list = 0;
+      Span sp("dibr_tile_soft_bwd_kernel<all tiles>", st);
       dibr_tile_soft_bwd_kernel<<<persistent, kThreads, 0, st>>>(a);
     } else {
       // forward left the bins, the hit cache and the list of tiles it could not cache
       a.from_list = 1;
-      if (s.pool_tiles > 0) soft_bwd_dense_kernel<<<(unsigned)s.pool_tiles, kThreads, 0, st>>>(a);
+      if (s.pool_tiles > 0) {
+        Span sp("soft_bwd_dense_kernel", st);
+        soft_bwd_dense_kernel<<<(unsigned)s.pool_tiles, kThreads, 0, st>>>(a);
+      }
+      Span sp("dibr_tile_soft_bwd_kernel<leftovers>", st);
       dibr_tile_soft_bwd_kernel<<<persistent, kThreads, 0, st>>>(a);
     }
     return (int)cudaGetLastError();
@@ -2104,6 +2496,7 @@ int dibr_b200_soft_mask_backward(int batch, int num_faces, int height, int width
   a.prob = close_face_prob; a.cidx = close_face_idx; a.ctype = close_face_dist_type;
   a.xy = face_vertices_image; a.grad_xy = grad_face_vertices_image;
   const int64_t P = (int64_t)batch * height * width;
+  Span sp("soft_bwd_lists_kernel", st);
   soft_bwd_lists_kernel<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(a);
   return (int)cudaGetLastError();
 }

@@ -124,12 +124,17 @@ class OverlappedGradAllGather:
     there (asynchronously, on the process group's stream) and travels while the soft-mask
     branch computes; ``grad_face_vertices_image`` follows at the end.
 
-        with OverlappedGradAllGather(batch) as gather:
-            torch.autograd.backward([feat, soft_mask], [g_feat, g_mask])
+        feat, soft_mask, face_idx = dibr_rasterization(...)
+        gather = OverlappedGradAllGather(batch).attach(soft_mask)     # this node only
+        torch.autograd.backward([feat, soft_mask], [g_feat, g_mask])
         full_g_fvi, full_g_ff = gather.finish(face_vertices_image.grad)
 
-    Equal shards only (``batch`` = world size x local views).  Works the same through
-    ``kaolin_b200.render.mesh._host.backward`` (the C-ABI call).
+    The hook is per call: ``attach`` stores it on the autograd node of that one
+    ``dibr_rasterization`` call (other DIB-R backward passes, on this or another device
+    or thread, are not affected); through the C-ABI path pass ``gather.hook`` as
+    ``_host.backward(..., feature_grad_hook=gather.hook)``.  ``finish`` waits for the
+    asynchronous gather, so the local gradient buffer is not touched by NCCL after it
+    returns.  Equal shards only (``batch`` = world size x local views).
     """
 
     def __init__(self, batch, group=None):
@@ -141,27 +146,33 @@ class OverlappedGradAllGather:
         self.work = None
         self.full_ff = None
         self.local_ff = None
-        self._prev = None
 
-    def _on_feature_grad(self, g_ff):
+    def hook(self, g_ff):
+        """Called by the fused backward between its two branches with the final fp32
+        ``grad_face_features`` of the local views."""
         if self.work is not None:
             raise RuntimeError("OverlappedGradAllGather covers one backward call")
         if g_ff.shape[0] * self.world != self.batch:
             raise ValueError(f"local gradient has {g_ff.shape[0]} views, expected {self.batch // self.world}")
-        self.local_ff = g_ff
+        self.local_ff = g_ff          # kept alive until finish(): NCCL reads it asynchronously
         self.full_ff = torch.empty((self.batch,) + tuple(g_ff.shape[1:]), dtype=g_ff.dtype, device=g_ff.device)
         self.work = dist.all_gather_into_tensor(self.full_ff, g_ff, group=self.group, async_op=True)
 
-    def __enter__(self):
-        from .render.mesh import _host
-        self._prev = _host.FEATURE_GRAD_HOOK
-        _host.FEATURE_GRAD_HOOK = self._on_feature_grad
+    def attach(self, output):
+        """Registers the hook on the autograd node that produced ``output`` (the soft mask
+        or the features of ONE ``dibr_rasterization`` call).  Returns self."""
+        node = getattr(output, "grad_fn", None)
+        seen = 0
+        while node is not None and not type(node).__name__.startswith("DibrRasterizationB200") and seen < 4:
+            # e.g. a slice of the feature image (list/tuple face_features): step to its producer
+            nxt = [fn for fn, _ in node.next_functions if fn is not None]
+            node = nxt[0] if len(nxt) == 1 else None
+            seen += 1
+        if node is None or not type(node).__name__.startswith("DibrRasterizationB200"):
+            raise ValueError("attach() needs an output of kaolin_b200.render.mesh.dibr_rasterization "
+                             "that requires grad")
+        node.feature_grad_hook = self.hook
         return self
-
-    def __exit__(self, *exc):
-        from .render.mesh import _host
-        _host.FEATURE_GRAD_HOOK = self._prev
-        return False
 
     def finish(self, g_fvi, g_ff=None):
         """Gathers ``g_fvi`` and returns (full_g_fvi, full_g_ff).  If the backward did not go
@@ -174,6 +185,6 @@ class OverlappedGradAllGather:
         elif g_ff is not None:
             full_ff = all_gather_view_grads([g_ff], self.batch, self.group)[0]
         else:
-            raise RuntimeError("no feature gradient was produced inside the context and none was passed")
+            raise RuntimeError("no feature gradient was produced by the attached backward and none was passed")
         self.work = self.full_ff = self.local_ff = None
         return full_fvi, full_ff

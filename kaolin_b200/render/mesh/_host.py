@@ -104,11 +104,6 @@ def forward(mode, height, width, fvz, fvi, ff, fnz, valid_u8, multiplier, eps,
     return feat, idx, wts, soft, ws
 
 
-# Called as hook(g_ff) between the two branches of a fused backward, when set (see
-# kaolin_b200.multi_gpu.OverlappedGradAllGather): grad_face_features is final after the
-# rasterize branch, so its all-gather can travel while the soft-mask branch runs.
-FEATURE_GRAD_HOOK = None
-
 
 def _backward_call(B, F, height, width, D, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps,
                    sigmainv, boxlen_m, knum, g_fvi, g_ff, ws, ws_bytes, flags, dev):
@@ -125,26 +120,32 @@ def _backward_call(B, F, height, width, D, g_feat, g_soft, face_idx, wts, soft, 
 
 
 def backward(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps,
-             sigmainv, boxlen_m, knum, ws, bins_valid):
+             sigmainv, boxlen_m, knum, ws, bins_valid, feature_grad_hook=None):
+    """Calls dibr_b200_backward; returns (grad_face_vertices_image, grad_face_features fp32).
+
+    ``feature_grad_hook`` (per call — there is no process-global state): called as
+    ``hook(g_ff)`` between the two branches of a fused backward.  grad_face_features is
+    final after the rasterize branch, so e.g. its all-gather can travel while the
+    soft-mask branch runs (kaolin_b200.multi_gpu.OverlappedGradAllGather)."""
     dev = fvi.device
     B, F = fvi.shape[0], fvi.shape[1]
     D = 0 if ff is None else ff.shape[-1]
     g_fvi = torch.empty_like(fvi)
     # grad_face_features is accumulated (atomics) in fp32 whatever the storage type
     g_ff = torch.empty(ff.shape, dtype=torch.float32, device=dev) if ff is not None else None
-    if g_soft is None:
-        ws, ws_bytes, bins_valid = None, 0, False   # the rasterize branch needs no scratch
-    else:
-        if ws is None:
-            ws = workspace(B, B * F, height, width, dev)
-            bins_valid = False
-        ws_bytes = ws.numel()
+    # The workspace carries forward's bins / hit cache (soft-mask branch, bins_valid) and the
+    # per-face records of the row-walk rasterize backward; without forward state a fresh
+    # minimum-size one serves both.
+    if ws is None:
+        ws = workspace(B, B * F, height, width, dev)
+        bins_valid = False
+    ws_bytes = ws.numel()
     flags = _lib.BINS_VALID if bins_valid else 0
-    hook = FEATURE_GRAD_HOOK
+    hook = feature_grad_hook
     if hook is not None and g_feat is not None and g_soft is not None and D > 0:
         # two calls: rasterize branch (g_ff final -> hook), then the soft-mask branch added on top
         _backward_call(B, F, height, width, D, g_feat, None, face_idx, wts, None, fvi, ff, multiplier, eps,
-                       sigmainv, boxlen_m, knum, g_fvi, g_ff, None, 0, 0, dev)
+                       sigmainv, boxlen_m, knum, g_fvi, g_ff, ws, ws_bytes, 0, dev)
         hook(g_ff)
         _backward_call(B, F, height, width, D, None, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps,
                        sigmainv, boxlen_m, knum, g_fvi, None, ws, ws_bytes, flags | _lib.ACCUMULATE, dev)

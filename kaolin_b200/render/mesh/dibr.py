@@ -4,7 +4,8 @@
 kernel (rasterize + soft mask share the face binning), the backward adds the
 rasterize and soft-mask gradients of ``face_vertices_image`` in place of the
 reference's two nodes + autograd sum.  Results are identical to
-calling ``rasterize`` then ``dibr_soft_mask`` (tests/test_api_gpu.py).
+calling ``rasterize`` then ``dibr_soft_mask``
+(tests/test_parity_gpu.py::test_composition_equals_separate_calls).
 """
 import torch
 from torch.autograd import Function
@@ -86,8 +87,10 @@ class DibrRasterizationB200(Function):
         height, width, multiplier, eps, sigmainv, boxlen_m, knum = ctx.params
         g_feat = None if grad_features is None else grad_features.contiguous()
         g_soft = None if grad_soft_mask is None else grad_soft_mask.contiguous()
+        # per-node hook (set on this node by OverlappedGradAllGather.attach, never global)
         g_fvi, g_ff = _host.backward(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff,
-                                     multiplier, eps, sigmainv, boxlen_m, knum, ctx.ws, True)
+                                     multiplier, eps, sigmainv, boxlen_m, knum, ctx.ws, True,
+                                     feature_grad_hook=getattr(ctx, "feature_grad_hook", None))
         g_ff = g_ff.to(ff.dtype)      # fp32 accumulation; autograd wants the input's dtype (bf16 features)
         return None, None, None, g_fvi, g_ff, None, None, None, None, None, None, None
 

@@ -91,18 +91,21 @@ def _overlap_worker(rank, world, batch, port, ok):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        from kaolin_b200.render.mesh import _host
         g, f = _fake_grads(batch, 5)
         lg, lf = shard_views([g, f], rank, world)
-        with OverlappedGradAllGather(batch) as gather:
-            assert _host.FEATURE_GRAD_HOOK is not None
-            _host.FEATURE_GRAD_HOOK(lf.clone())      # what the fused backward does between its branches
-        assert _host.FEATURE_GRAD_HOOK is None
+        gather = OverlappedGradAllGather(batch)
+        gather.hook(lf.clone())                      # what the fused backward does between its branches
         full_g, full_f = gather.finish(lg.clone())
-        # no hook call inside the context: the feature gradient is gathered in finish()
-        with OverlappedGradAllGather(batch) as gather2:
-            pass
+        # the hook never ran: the feature gradient is gathered in finish()
+        gather2 = OverlappedGradAllGather(batch)
         full_g2, full_f2 = gather2.finish(lg.clone(), lf.clone())
+        # attach() refuses tensors that are not outputs of dibr_rasterization
+        try:
+            OverlappedGradAllGather(batch).attach(torch.zeros(3, requires_grad=True) * 2)
+            attached = True
+        except ValueError:
+            attached = False
+        assert not attached
         ok[rank] = int(torch.equal(full_g, g) and torch.equal(full_f, f)
                        and torch.equal(full_g2, g) and torch.equal(full_f2, f))
     finally:

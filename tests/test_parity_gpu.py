@@ -28,7 +28,17 @@ DEV = "cuda"
 # double-precision accumulation that noise is ~1e-6 of the gradient's scale for
 # meshes and reaches ~1.5e-5 on the overlapping-soup scene (thousands of pixels per
 # face); the reference's own kernels show the same deviation (printed below).
-GRAD_REL = 3e-5
+GRAD_REL = 3e-5          # against the double-accumulating CPU oracle only
+GRAD_REL_REF = 1e-5      # against the reference's own CUDA kernels (north_star: "within 1e-5")
+
+
+def assert_grad_close(a, ref, tol=GRAD_REL_REF, what="grad"):
+    """max-normalised error <= tol AND element-wise allclose(rtol=tol, atol=tol * scale)."""
+    scale = max(float(np.abs(ref).max()), 1e-30)
+    e = float(np.abs(a - ref).max() / scale)
+    assert e <= tol, (what, e)
+    assert np.allclose(a, ref, rtol=tol, atol=tol * scale), what
+    return e
 
 
 def T(a, grad=False):
@@ -106,8 +116,8 @@ def test_fused_dibr_vs_reference_cuda(name):
     assert np.array_equal(idx, N(r["face_idx"]))
     np.testing.assert_allclose(feat, N(r["features"]), rtol=0, atol=1e-5)
     np.testing.assert_allclose(soft, N(r["soft_mask"]), rtol=0, atol=1e-5)
-    assert rel_err(g_fvi, N(r["grad_fvi"])) <= 3e-5     # both sides accumulate in fp32 atomics
-    assert rel_err(g_ff, N(r["grad_ff"])) <= 3e-5
+    assert_grad_close(g_fvi, N(r["grad_fvi"]), what="grad_fvi")     # both sides accumulate in fp32 atomics
+    assert_grad_close(g_ff, N(r["grad_ff"]), what="grad_ff")
 
 
 CONFIG_CASES = {
@@ -146,7 +156,8 @@ def test_baseline_configs_vs_reference_cuda(name):
     e_ff = rel_err(N(t_ff.grad), N(r["grad_ff"]))
     print(f"\n[{name}] face_idx exact; soft_mask bit-equal {bit_equal:.6f}; grad rel err fvi {e_xy:.2e} ff {e_ff:.2e}")
     assert bit_equal > 0.9999
-    assert e_xy <= 3e-5 and e_ff <= 3e-5
+    assert_grad_close(N(t_fvi.grad), N(r["grad_fvi"]), what="grad_fvi")
+    assert_grad_close(N(t_ff.grad), N(r["grad_ff"]), what="grad_ff")
 
 
 def test_two_call_backward_with_feature_grad_hook_equals_fused():
@@ -164,11 +175,9 @@ def test_two_call_backward_with_feature_grad_hook_equals_fused():
     for hook in (None, lambda g: seen.append(g.clone())):
         t_fvi, t_ff = T(fvi, True), T(ff, True)
         feat, soft, idx = dibr_rasterization(H, W, T(fvz), t_fvi, t_ff, T(fnz))
-        prev, _host.FEATURE_GRAD_HOOK = _host.FEATURE_GRAD_HOOK, hook
-        try:
-            torch.autograd.backward([feat, soft], [g_feat, g_soft])
-        finally:
-            _host.FEATURE_GRAD_HOOK = prev
+        if hook is not None:
+            soft.grad_fn.feature_grad_hook = hook       # per-node state (what OverlappedGradAllGather.attach sets)
+        torch.autograd.backward([feat, soft], [g_feat, g_soft])
         grads.append((N(t_fvi.grad), N(t_ff.grad)))
     assert len(seen) == 1 and rel_err(N(seen[0]), grads[1][1]) == 0.0   # g_ff was final at the hook
     assert rel_err(grads[1][0], grads[0][0]) <= 1e-6                      # float atomics: order only
@@ -227,7 +236,7 @@ def test_bf16_feature_storage_vs_reference_cuda(D):
     assert torch.equal(idx, r["face_idx"])
     assert torch.equal(soft, r["soft_mask"])
     assert torch.equal(feat, r["features"].to(torch.bfloat16))            # one rounding, on store
-    assert rel_err(N(t_fvi.grad), N(r["grad_fvi"])) <= 3e-5
+    assert rel_err(N(t_fvi.grad), N(r["grad_fvi"])) <= GRAD_REL_REF
     assert rel_err(N(t_ff.grad.float()), N(r["grad_ff"])) <= 2.0 ** -8      # bf16 rounding of the result
     # the C ABI returns the fp32 accumulation itself
     feat2, idx2, wts2, soft2, ws = _host.forward(3, H, W, t_fvz, t_fvi.detach(), ff16, t_fnz, None, 1000., 1e-8,
@@ -235,8 +244,8 @@ def test_bf16_feature_storage_vs_reference_cuda(D):
     g_fvi, g_ff = _host.backward(H, W, g_feat16, g_soft, idx2, wts2, soft2, t_fvi.detach(), ff16, 1000., 1e-8,
                                  7000., 0.02 * 1000., 30, ws, True)
     assert g_ff.dtype == torch.float32 and torch.equal(feat2, feat)
-    assert rel_err(N(g_ff), N(r["grad_ff"])) <= 3e-5
-    assert rel_err(N(g_fvi), N(r["grad_fvi"])) <= 3e-5
+    assert rel_err(N(g_ff), N(r["grad_ff"])) <= GRAD_REL_REF
+    assert rel_err(N(g_fvi), N(r["grad_fvi"])) <= GRAD_REL_REF
     # rasterize alone, tuple features
     (a, b), idx3 = rasterize(H, W, t_fvz, t_fvi.detach(), [ff16[..., :2], ff16[..., 2:]], t_fnz >= 0.)
     assert torch.equal(idx3, idx) and torch.equal(torch.cat([a, b], -1), feat)
