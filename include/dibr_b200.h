@@ -109,7 +109,7 @@ int dibr_b200_forward(
  *                 grad_face_features is only touched when grad_features is given.
  *  workspace      may be NULL when grad_soft_mask is NULL.  When it is at least
  *                 dibr_b200_workspace_bytes() the rasterize branch (fp32 features, D <= 4,
- *                 width a multiple of 8) runs the row-walk kernel, which scatters into padded
+ *                 width a multiple of 4) runs the row-walk kernel, which scatters into padded
  *                 per-face records in the workspace with 16-byte vector reductions; otherwise
  *                 the warp-reduction kernel scatters straight into the outputs.
  */

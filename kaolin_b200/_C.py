@@ -4,7 +4,8 @@ return structure and error behaviour, implemented by libdibr_b200.so.
 
 This is what makes the library a drop-in *below* the reference's own Python
 wrappers: ``kaolin.render.mesh.rasterization`` / ``.dibr`` run unmodified with
-``kaolin._C`` replaced by this module (tests/test_reference_wrappers_gpu.py).
+``kaolin._C`` replaced by this module (tests/test_reference_wrappers.py: arity / dispatch on CPU,
+results on the GPU).
 """
 import ctypes
 import types
@@ -41,6 +42,24 @@ def _check_all(func, named, float_dtype=torch.float32):
     return dev
 
 
+def _fp64_via_fp32(op):
+    """The reference's operators dispatch float and double (AT_DISPATCH_FLOATING_TYPES,
+    rasterization_cuda.cu:218/427, dibr_soft_mask_cuda.cu:205/376); the kernels here are fp32.
+    Double callers are served by casting: float64 inputs -> float32, the op, floating-point
+    outputs -> float64 (fp32 rounding applies; see render/mesh/_host.py:wants_fp64)."""
+    import functools
+
+    @functools.wraps(op)
+    def wrapped(*args):
+        if not any(isinstance(a, torch.Tensor) and a.dtype == torch.float64 for a in args):
+            return op(*args)
+        out = op(*[a.to(torch.float32) if isinstance(a, torch.Tensor) and a.dtype == torch.float64 else a
+                   for a in args])
+        cast = lambda t: t.to(torch.float64) if isinstance(t, torch.Tensor) and t.dtype == torch.float32 else t
+        return [cast(t) for t in out] if isinstance(out, (list, tuple)) else cast(out)
+    return wrapped
+
+
 def _check_size(func, name, t, shape):
     if tuple(t.shape) != tuple(shape):
         raise RuntimeError(f"{func}: expected tensor of size {list(shape)} for argument {name}, "
@@ -54,6 +73,7 @@ def _workspace(batch, total_faces, height, width, dev):
     return torch.empty(n, dtype=torch.uint8, device=dev)
 
 
+@_fp64_via_fp32
 def packed_rasterize_forward_cuda(height, width, face_vertices_z, face_vertices_image,
                                   face_bboxes, face_features, first_idx_face_per_mesh,
                                   multiplier, eps):
@@ -87,6 +107,7 @@ def packed_rasterize_forward_cuda(height, width, face_vertices_z, face_vertices_
     return [out, idx, w]
 
 
+@_fp64_via_fp32
 def rasterize_backward_cuda(grad_interpolated_features, interpolated_features, selected_face_idx,
                             output_weights, face_vertices_image, face_features, eps):
     """rasterization.cpp:106-168 -> [grad_face_vertices_image, grad_face_features]."""
@@ -115,6 +136,7 @@ def rasterize_backward_cuda(grad_interpolated_features, interpolated_features, s
     return [g_xy, g_ff]
 
 
+@_fp64_via_fp32
 def dibr_soft_mask_forward_cuda(face_vertices_image, face_large_bboxes, selected_face_idx,
                                 sigmainv, knum, multiplier):
     """dibr_soft_mask.cpp:48-108 -> [soft_mask, close_face_prob, close_face_idx, close_face_dist_type]."""
@@ -141,6 +163,7 @@ def dibr_soft_mask_forward_cuda(face_vertices_image, face_large_bboxes, selected
     return [soft, prob, cidx, ctype]
 
 
+@_fp64_via_fp32
 def dibr_soft_mask_backward_cuda(grad_soft_mask, soft_mask, selected_face_idx, close_face_prob,
                                  close_face_idx, close_face_dist_type, face_vertices_image,
                                  sigmainv, multiplier):

@@ -11,8 +11,9 @@ import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(CSRC, "libdibr_b200.so")
-SOURCES = [os.path.join(CSRC, "dibr_b200.cu")]
+# DIBR_B200_LIB: an alternative build of the same sources (A/B experiments on the GPU box only)
+LIB_PATH = os.environ.get("DIBR_B200_LIB") or os.path.join(CSRC, "libdibr_b200.so")
+SOURCES = [os.path.join(CSRC, "dibr_b200.cu"), os.path.join(CSRC, "mesh_pipeline.cu")]
 HEADERS = [os.path.join(CSRC, "dibr_math.cuh"),
            os.path.join(_HERE, "..", "include", "dibr_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -30,6 +31,7 @@ _i = ctypes.c_int
 _i64 = ctypes.c_int64
 _f = ctypes.c_float
 _sz = ctypes.c_size_t
+_fp3 = ctypes.POINTER(ctypes.c_float)      # HOST pointer to 3 floats (camera_proj)
 
 SIGNATURES = {
     "dibr_b200_version": (_i, []),
@@ -53,6 +55,14 @@ SIGNATURES = {
                                          _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dibr_b200_soft_mask_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                           _f, _f, _vp, _vp]),
+    # the steps either side of the rasterizer (csrc/mesh_pipeline.cu)
+    "dibr_b200_prepare_vertices_forward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _fp3, _vp, _vp, _vp, _vp]),
+    "dibr_b200_prepare_vertices_backward": (_i, [_i, _i, _i, _vp, _vp, _vp, _vp, _vp, _fp3, _vp, _vp, _vp,
+                                                 _vp, _vp]),
+    "dibr_b200_texture_mapping_forward": (_i, [_i, _i64, _i, _i, _i, _vp, _vp, _i, _vp, _vp]),
+    "dibr_b200_texture_mapping_backward": (_i, [_i, _i64, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
+    "dibr_b200_mask_iou_forward": (_i, [_i, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "dibr_b200_mask_iou_backward": (_i, [_i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
 }
 
 

@@ -1228,6 +1228,337 @@ __global__ void __launch_bounds__(kThreads, 6) dibr_tile_fwd_kernel(const __grid
   }
 }
 
+// ---------------------------------------------------------------------------
+// Forward tile kernel, second generation.  Same results as dibr_tile_fwd_kernel; what changed
+// is where the instructions go (ncu, round 1: 750 warp instructions per 8x4 pixel block, of
+// which ~300 were per-tile fixed work shared by only 8 warps, and 6.9 hit-walk iterations for
+// the slowest lane of a block):
+//   * a CTA owns S x S screen tiles (S = 2: 32x32 px) and stages their candidates ONCE
+//     (bin table, TMA rounds, tile cull, face gather, bit matrices); the S*S sub-tiles are
+//     then rasterized one after the other with the round-1 thread -> pixel mapping, so the
+//     soft-mask work list, the hit cache and every consumer keep their 16x16 tiles;
+//   * a face is inserted in up to 2x2 level-0 bins; with several of them under one CTA it is
+//     taken from the first of its bins inside the CTA only (integer test on its rectangle);
+//   * conservative triangle-vs-block culling: while staging, each candidate gets its three
+//     edge functions as AFFINE functions of the CTA-local pixel index (computed in double,
+//     oriented so that inside is >= 0), with a margin that dominates the fp32 rounding of the
+//     reference's own evaluation.  A warp (8x4 block) lets lane j test candidate j at the
+//     block's extreme corners; candidates that are provably outside one edge at every pixel
+//     of the block are dropped (8.5 -> 4.9 candidates per block on the benchmark mesh);
+//   * the surviving candidates are visited in a WARP-UNIFORM loop (broadcast shared-memory
+//     reads, no per-lane bit walk); the per-pixel decision is still the exact reference
+//     arithmetic of raster_weights, so face_idx stays bit-exact.
+template <int S>
+struct FwdSmem {
+  static constexpr int kSide = kTile * S;
+  static constexpr int kSubs = S * S;
+  int4 stage[2][kChunk];
+  float4 cxy0[kChunk];
+  float4 cz[kChunk];
+  float2 cxy1[kChunk];
+  int cface[kChunk];
+  float4 cedge[kChunk][3];                 // per edge: {A + margin, B, C, -}: s*u_i ~ A + B*lx + C*ly
+  uint32_t colbits[kChunk / 32][kSide];
+  uint32_t rowbits[kChunk / 32][kSide];
+  unsigned long long bar[2];
+  BinRef bin0[2][kSubs];                   // level-0 bins of the sub-tiles (set, sub)
+  BinRef bin[2][kMaxLevels];               // levels >= 1 (entry 0 unused)
+  int any_uncovered[kSubs], warps_done[kSubs];
+  unsigned uncmask[kSubs][kThreads / 32];
+};
+
+// Affine, sign-normalised edge functions of one face over a CTA tile whose pixel (0,0) has the
+// centre (X0, Y0) and whose pixel pitch is (dx, -dy).  See the kernel comment for the contract:
+// s*u_i(pixel) computed by the reference in fp32 is < 0 wherever A' + B*lx + C*ly < 0.
+__device__ __noinline__ void make_edge_tests(const float v[6], double X0, double Y0, double dx, double dy,
+                                                int side, float4 out[3]) {
+  const double ax = v[0], ay = v[1], bx = v[2], by = v[3], cx = v[4], cy = v[5];
+  const double n = (bx - ax) * (cy - ay) - (by - ay) * (cx - ax);   // u0 + u1 + u2, exact up to 2^-53
+  const double sgn = n < 0.0 ? -1.0 : 1.0;
+  const double ext_x = side * dx, ext_y = side * dy;
+  const double Rx = fmax(fmax(fabs(ax - X0), fabs(bx - X0)), fabs(cx - X0)) + ext_x;
+  const double Ry = fmax(fmax(fabs(ay - Y0), fabs(by - Y0)), fabs(cy - Y0)) + ext_y;
+  const double coord = fabs(X0) + fabs(Y0) + ext_x + ext_y;
+  const double px[3] = {bx, cx, ax}, py[3] = {by, cy, ay};          // u0: P=b,Q=c  u1: P=c,Q=a  u2: P=a,Q=b
+  const double qx[3] = {cx, ax, bx}, qy[3] = {cy, ay, by};
+  double A[3], B[3], C[3], marg = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    const double ux = py[i] - qy[i], uy = qx[i] - px[i];            // du/dx, du/dy
+    A[i] = sgn * ((px[i] - X0) * (qy[i] - Y0) - (py[i] - Y0) * (qx[i] - X0));
+    B[i] = sgn * ux * dx;
+    C[i] = -sgn * uy * dy;
+    const double m = 1.9073486328125e-06 * Rx * Ry                                  // 2^-19: fp32 products / fma
+                     + 4.76837158203125e-07 * coord * (fabs(ux) + fabs(uy))          // 2^-21: pixel-centre rounding
+                     + 9.5367431640625e-07 * (fabs(A[i]) + side * (fabs(B[i]) + fabs(C[i])));  // 2^-20: the block test itself
+    marg = fmax(marg, m);
+  }
+  marg = 4.0 * marg + 1e-6;
+  // the orientation must be certain and every quantity in range for the sign argument
+  const bool ok = fabs(n) > 16.0 * marg && Rx < 268435456.0 && Ry < 268435456.0 && coord < 268435456.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+    out[i] = ok ? make_float4((float)(A[i] + marg), (float)B[i], (float)C[i], 0.f)
+                : make_float4(INFINITY, 0.f, 0.f, 0.f);           // never culled (also NaN / Inf input)
+}
+
+#ifndef DIBR_FWD2_MINB
+#define DIBR_FWD2_MINB 6
+#endif
+template <bool RASTER, bool SOFT, bool KLISTS, typename FT, int S>
+__global__ void __launch_bounds__(kThreads, DIBR_FWD2_MINB) dibr_fwd2_kernel(const __grid_constant__ FwdArgs a) {
+  using SM = FwdSmem<S>;
+  constexpr int kSubs = S * S;
+  constexpr int kSide = kTile * S;
+  constexpr int kPieces = kSubs + kMaxLevels - 1;
+  __shared__ __align__(128) SM sm;
+  const Scene& s = a.s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int b = blockIdx.z;
+  const int ctx0 = blockIdx.x * S, cty0 = blockIdx.y * S;   // first 16x16 tile of the CTA
+  const int cta_x0 = ctx0 * kTile, cta_y0 = cty0 * kTile;
+  const int64_t fbase = view_fbase(s, b);
+
+  if (RASTER && tid == 32) { mbar_init(&sm.bar[0], 1); mbar_init(&sm.bar[1], 1); mbar_fence_init(); }
+  if (tid >= 64 && tid < 64 + kSubs) { sm.any_uncovered[tid - 64] = 0; sm.warps_done[tid - 64] = 0; }
+  if (tid < 2 * kSubs) {
+    const int set = tid / kSubs, sub = tid % kSubs;
+    const int tx = ctx0 + sub % S, ty = cty0 + sub / S;
+    BinRef r; r.ptr = nullptr; r.n = 0;
+    if (tx < s.ntx[0] && ty < s.nty[0]) r = tile_bin(s, b, tx, ty, fbase, set, 0);
+    sm.bin0[set][sub] = r;
+  } else if (tid >= 96 && tid < 96 + 16) {
+    const int set = (tid - 96) >> 3, l = (tid - 96) & 7;
+    if (l < kMaxLevels) {
+      BinRef r; r.ptr = nullptr; r.n = 0;
+      if (l >= 1 && l < s.L) r = tile_bin(s, b, ctx0, cty0, fbase, set, l);
+      sm.bin[set][l] = r;
+    }
+  }
+  __syncthreads();
+
+  // the tight bins above the CTA tile as one virtual list: S*S level-0 pieces, then levels 1..
+  auto pn = [&](int p) { return p < kSubs ? sm.bin0[0][p].n : sm.bin[0][p - kSubs + 1].n; };
+  int total = 0;
+  if (RASTER) {
+#pragma unroll
+    for (int p = 0; p < kPieces; ++p) total += pn(p);
+  }
+  const int nrounds = (total + kChunk - 1) / kChunk;
+  int issued = 0, waited = 0;       // staging iterations (thread 0 / everyone): buffer = n & 1, parity = (n >> 1) & 1
+  auto issue = [&](int k) {          // thread 0 only
+    const int lo = k * kChunk, hi = min(total, lo + kChunk);
+    unsigned long long* bar = &sm.bar[issued & 1];
+    mbar_expect_tx(bar, (uint32_t)(hi - lo) * 16u);
+    int start = 0;
+#pragma unroll
+    for (int p = 0; p < kPieces; ++p) {
+      const int4* ptr = p < kSubs ? sm.bin0[0][p].ptr : sm.bin[0][p - kSubs + 1].ptr;
+      const int np = pn(p);
+      const int x = max(lo, start), y = min(hi, start + np);
+      if (y > x) tma_load_1d(&sm.stage[issued & 1][x - lo], ptr + (x - start), (uint32_t)(y - x) * 16u, bar);
+      start += np;
+    }
+    ++issued;
+  };
+
+  bool staged = false;
+
+  for (int sub = 0; sub < kSubs; ++sub) {
+    const int sx = sub % S, sy = sub / S;
+    const int tx = ctx0 + sx, ty = cty0 + sy;
+    if (tx >= s.ntx[0] || ty >= s.nty[0]) continue;   // uniform: sub-tile outside the image
+    const int lx = ((warp & 1) << 3) | (lane & 7);     // each warp owns an 8x4 pixel block
+    const int ly = ((warp >> 1) << 2) | (lane >> 3);
+    const int px = tx * kTile + lx, py = ty * kTile + ly;
+    const bool in_img = px < s.W && py < s.H;
+    const int64_t pix = ((int64_t)b * s.H + py) * s.W + px;
+    int best_f;
+    if (RASTER) {
+      RasterOut o;
+      o.z = -INFINITY; o.f = -1; o.w0 = o.w1 = o.w2 = 0.f;
+      if (total > 0) {
+        const float x0 = pix_x(s.grid, px), y0 = pix_y(s.grid, py);
+        const int clx = sx * kTile + lx, cly = sy * kTile + ly;
+        const float fbx0 = (float)(sx * kTile + ((warp & 1) << 3)), fbx1 = fbx0 + 7.f;
+        const float fby0 = (float)(sy * kTile + ((warp >> 1) << 2)), fby1 = fby0 + 3.f;
+        for (int k = 0; k < nrounds; ++k) {
+          const int cnt = min(kChunk, total - k * kChunk);
+          if (!(staged && nrounds == 1)) {
+            // ---- stage round k: TMA -> cull against the CTA tile -> face records, edge tests, bit matrices
+            if (tid == 0) {
+              if (k == 0) issue(0);
+              if (k + 1 < nrounds) issue(k + 1);   // its buffer was released by the barrier ending round k-1
+            }
+            const int buf = waited & 1;
+            mbar_wait(&sm.bar[buf], (uint32_t)((waited >> 1) & 1));
+            ++waited;
+            uint32_t cm = 0, rm = 0;
+            if (tid < cnt) {
+              const int4 e = sm.stage[buf][tid];
+              const int x_lo = e.y & 0xffff, x_hi = (int)((unsigned)e.y >> 16);
+              const int y_lo = e.z & 0xffff, y_hi = (int)((unsigned)e.z >> 16);
+              bool take = true;
+              if (S > 1) {
+                // level-0 pieces: the face is also in the neighbouring bins it spans; take it from
+                // the first of its bins inside this CTA only
+                const int vi = k * kChunk + tid;
+                int start = 0;
+#pragma unroll
+                for (int p = 0; p < kSubs; ++p) {
+                  const int np = pn(p);
+                  if (vi >= start && vi < start + np)
+                    take = (ctx0 + p % S) == max(x_lo >> 4, ctx0) && (cty0 + p / S) == max(y_lo >> 4, cty0);
+                  start += np;
+                }
+              }
+              if (take) {
+                const int cx0 = max(x_lo - cta_x0, 0), cx1 = min(x_hi - cta_x0, kSide);
+                const int cy0 = max(y_lo - cta_y0, 0), cy1 = min(y_hi - cta_y0, kSide);
+                if (cx1 > cx0 && cy1 > cy0) {
+                  cm = (uint32_t)(((1ull << cx1) - 1ull) & ~((1ull << cx0) - 1ull));
+                  rm = (uint32_t)(((1ull << cy1) - 1ull) & ~((1ull << cy0) - 1ull));
+                }
+              }
+              if (cm) {
+                const int64_t g = fbase + e.x;
+                float v[6];
+                load_xy(s, g, v);
+                const float* zp = s.z + g * 3;
+                sm.cxy0[tid] = make_float4(v[0], v[1], v[2], v[3]);
+                sm.cxy1[tid] = make_float2(v[4], v[5]);
+                sm.cz[tid] = make_float4(__ldg(zp), __ldg(zp + 1), __ldg(zp + 2), 0.f);
+                sm.cface[tid] = e.x;
+                float4 et[3];
+                make_edge_tests(v, (double)pix_x(s.grid, cta_x0), (double)pix_y(s.grid, cta_y0),
+                                2.0 * (double)s.grid.inv_w, 2.0 * (double)s.grid.inv_h, kSide, et);
+                sm.cedge[tid][0] = et[0]; sm.cedge[tid][1] = et[1]; sm.cedge[tid][2] = et[2];
+              }
+            }
+            if ((tid & ~31) < cnt) {
+              // transpose the rectangle masks of this warp's 32 candidates into per-column / per-row words
+              const int g = tid >> 5;
+              if (__any_sync(kFull, cm != 0)) {
+                uint32_t mine_c = 0, mine_r = 0;
+#pragma unroll
+                for (int q = 0; q < kSide; ++q) {
+                  const uint32_t c = __ballot_sync(kFull, (cm >> q) & 1u);
+                  const uint32_t r = __ballot_sync(kFull, (rm >> q) & 1u);
+                  if (lane == (q & 31)) { mine_c = c; mine_r = r; }
+                }
+                if (lane < kSide) { sm.colbits[g][lane] = mine_c; sm.rowbits[g][lane] = mine_r; }
+              } else if (lane < kSide) {
+                sm.colbits[g][lane] = 0; sm.rowbits[g][lane] = 0;
+              }
+            }
+            __syncthreads();
+          }
+          // ---- rasterize this sub-tile against the staged round
+          const int ngroups = (cnt + 31) >> 5;
+          for (int g = 0; g < ngroups; ++g) {
+            const uint32_t mybits = sm.colbits[g][clx] & sm.rowbits[g][cly];
+            const uint32_t uni = __reduce_or_sync(kFull, mybits);   // candidates whose rectangle meets the block
+            if (!uni) continue;
+            bool keep = false;
+            if ((uni >> lane) & 1u) {                                 // lane j: candidate j against the block's corners
+              const float4 e0 = sm.cedge[(g << 5) + lane][0], e1 = sm.cedge[(g << 5) + lane][1],
+                           e2 = sm.cedge[(g << 5) + lane][2];
+              const float h0 = e0.x + fmaxf(e0.y * fbx0, e0.y * fbx1) + fmaxf(e0.z * fby0, e0.z * fby1);
+              const float h1 = e1.x + fmaxf(e1.y * fbx0, e1.y * fbx1) + fmaxf(e1.z * fby0, e1.z * fby1);
+              const float h2 = e2.x + fmaxf(e2.y * fbx0, e2.y * fbx1) + fmaxf(e2.z * fby0, e2.z * fby1);
+              keep = !(h0 < 0.f || h1 < 0.f || h2 < 0.f);
+            }
+            uint32_t surv = __ballot_sync(kFull, keep);
+            while (surv) {                                            // warp-uniform loop
+              const int jj = __ffs(surv) - 1;
+              surv &= surv - 1;
+              if (!((mybits >> jj) & 1u)) continue;
+              const int j = (g << 5) + jj;
+              const float4 q0 = sm.cxy0[j];
+              const float2 q1 = sm.cxy1[j];
+              float w0, w1, w2;
+              if (!raster_weights(a.rc, x0, y0, q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, w0, w1, w2)) continue;
+              const float4 zz = sm.cz[j];
+              const float zv = raster_depth(zz.x, zz.y, zz.z, w0, w1, w2);
+              const int f = sm.cface[j];
+              // reference: strict '>' in ascending face order == (z, lowest index) maximum
+              if (!(zv <= o.z) || (zv == o.z && f < o.f)) { o.z = zv; o.f = f; o.w0 = w0; o.w1 = w1; o.w2 = w2; }
+            }
+          }
+          if (nrounds > 1) __syncthreads();   // the next round overwrites the staged arrays
+        }
+        staged = true;
+      }
+      best_f = o.f;
+      if (in_img) {
+        a.idx[pix] = (int64_t)o.f;
+        float* wp = a.out_w + pix * 3;
+        wp[0] = o.w0; wp[1] = o.w1; wp[2] = o.w2;
+        FT* fp = static_cast<FT*>(a.out_feat) + pix * a.D;
+        const FT* feat = static_cast<const FT*>(a.feat);
+        if (a.D == 3) {  // the DIB-R tutorial shape (uv + mask), fully unrolled
+          float r[3] = {0.f, 0.f, 0.f};
+          if (o.f >= 0) {
+            const FT* ff = feat + (fbase + o.f) * 9;
+#pragma unroll
+            for (int d = 0; d < 3; ++d)
+              r[d] = raster_interp(Feat<FT>::ld(ff + d), Feat<FT>::ld(ff + 3 + d), Feat<FT>::ld(ff + 6 + d),
+                                   o.w0, o.w1, o.w2);
+          }
+          Feat<FT>::st(fp, r[0]); Feat<FT>::st(fp + 1, r[1]); Feat<FT>::st(fp + 2, r[2]);
+        } else if (o.f >= 0) {
+          const FT* ff = feat + (fbase + o.f) * 3 * a.D;
+          for (int d = 0; d < a.D; ++d)
+            Feat<FT>::st(fp + d, raster_interp(Feat<FT>::ld(ff + d), Feat<FT>::ld(ff + a.D + d),
+                                               Feat<FT>::ld(ff + 2 * a.D + d), o.w0, o.w1, o.w2));
+        } else {
+          for (int d = 0; d < a.D; ++d) Feat<FT>::st(fp + d, 0.f);
+        }
+      }
+    } else {
+      best_f = in_img ? (int)a.idx[pix] : 0;
+    }
+    if (SOFT) {
+      // defaults (covered: 1; uncovered with no neighbour: 1 - 1 = 0) and K-list padding; tiles
+      // where an uncovered pixel may lie under an enlarged face go to the soft-mask work list
+      const bool uncovered = in_img && best_f < 0;
+      if (in_img) {
+        a.out_soft[pix] = uncovered ? 0.0f : 1.0f;
+        if (KLISTS) {  // padding the reference gets from at::zeros / at::full(-1)
+          for (int k = 0; k < a.K; ++k) {
+            const int64_t o = pix * a.K + k;
+            a.kl.prob[o] = 0.f; a.kl.idx[o] = -1; a.kl.type[o] = 0;
+          }
+        }
+      }
+      // no CTA barrier: warps retire independently; the last one to finish files the tile
+      const unsigned wv = __ballot_sync(kFull, uncovered);
+      if (lane == 0) {
+        sm.uncmask[sub][warp] = wv;
+        if (wv) atomicOr(&sm.any_uncovered[sub], 1);
+        __threadfence_block();
+        if (atomicAdd(&sm.warps_done[sub], 1) == kThreads / 32 - 1 && atomicOr(&sm.any_uncovered[sub], 0)) {
+          const int nlarge = ((__ldg(s.tile_cnt + ((size_t)b * s.nty[0] + ty) * ((s.ntx[0] + 31) >> 5) + (tx >> 5)) >> (tx & 31)) & 1) +
+                             __ldg(s.view_flag + b);
+          if (nlarge > 0) {
+            // work-list record: everything the soft-mask kernels need to start without
+            // re-reading face_idx or the bin tables
+            int* rec = s.band_list + (size_t)atomicAdd(s.band_ctr, 1) * kBandRec;
+            const int4* ebase = s.entries + (size_t)4 * s.NF + 4 * fbase;
+            rec[0] = (b * s.nty[0] + ty) * s.ntx[0] + tx;
+            for (int q = 0; q < kThreads / 32; ++q) rec[1 + q] = (int)atomicOr(&sm.uncmask[sub][q], 0u);
+            for (int l = 0; l < kMaxLevels; ++l) {
+              const BinRef br = l == 0 ? sm.bin0[1][sub] : sm.bin[1][l];
+              rec[9 + 2 * l] = br.n > 0 ? (int)(br.ptr - ebase) : 0;
+              rec[10 + 2 * l] = br.n;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
 // Soft-mask forward over the work list (persistent CTAs).
 template <bool KLISTS>
 __global__ void __launch_bounds__(kThreads, 4) soft_tiles_fwd_kernel(const __grid_constant__ FwdArgs a) {
@@ -1645,7 +1976,7 @@ __global__ void __launch_bounds__(kThreads, 6) raster_bwd_kernel(const __grid_co
 
 // ---------------------------------------------------------------------------
 // Rasterize backward, ROW-WALK variant (the one the fused path uses when the feature
-// dim is 1..4 fp32 and the image width a multiple of 8).
+// dim is 1..4 fp32 and the image width a multiple of 4).
 //
 // Measured on B200 (scripts/microbench.cu): SHFL issues at 1 warp-instruction per
 // clock per SM (a quarter of the FFMA rate), and a vector reduction RED.E.ADD.F32x4
@@ -1658,22 +1989,26 @@ __global__ void __launch_bounds__(kThreads, 6) raster_bwd_kernel(const __grid_co
 //     per-face accumulator (acc[face][16] for D = 3: 64-byte records, 16-byte aligned) and
 //     reloads the face constants.  No shuffles, no match, no leader election;
 //   * the pixel streams (face_idx 8 B, weights 12 B, upstream gradient 4*D B per pixel) are
-//     staged per 8-column slab with 16-byte cp.async (LDGSTS) into rows padded to an odd
+//     staged per 4-column slab with 16-byte cp.async (LDGSTS) into rows padded to an odd
 //     number of 16-byte chunks, double buffered, and read back with LDS.128 (conflict free:
-//     8 consecutive rows cover the 32 banks);
+//     8 consecutive rows cover the 32 banks).  9 KB of shared memory and <= 100 registers per
+//     single-warp CTA keep ~20 warps per SM in flight (the first version, 8-column slabs at
+//     162 registers, ran 9 warps per SM at 47 % issue utilisation: ncu, profiles/r2_*);
 //   * raster_bwd_finalize_kernel unpacks acc into grad_face_vertices_image /
 //     grad_face_features (which therefore need no memset).
 // Per-pixel arithmetic is the reference's operation tree (dibr_math.cuh,
 // raster_backward_geom / _feature) with the face-constant factors hoisted; the only
 // change is g * (1 / k3^2) for g / k3^2 (<= 1 ulp per term).
-constexpr int kRwSlab = 8;   // columns per staged slab
+constexpr int kRwSlab = 4;   // columns per staged slab (= the 4-pixel block a lane reads with LDS.128)
 
 template <int DT>
 struct RwCfg {
-  static constexpr int kIdxPitch = 80;                          // 8 px * 8 B = 64 -> 5 chunks
-  static constexpr int kWPitch = 112;                           // 8 px * 12 B = 96 -> 7 chunks
-  static constexpr int kGRow = kRwSlab * DT * 4;
-  static constexpr int kGPitch = ((kGRow / 16) & 1) ? kGRow : kGRow + 16;
+  // rows padded to an ODD number of 16-byte chunks: 8 consecutive rows then cover all 32 banks
+  static constexpr int pad_odd(int bytes) { return ((bytes / 16) & 1) ? bytes : bytes + 16; }
+  static constexpr int kIdxPitch = pad_odd(kRwSlab * 8);        // 32 -> 48
+  static constexpr int kWPitch = pad_odd(kRwSlab * 12);         // 48
+  static constexpr int kGRow = kRwSlab * DT * 4;                // 16*D
+  static constexpr int kGPitch = pad_odd(kGRow);
   static constexpr int kStage = 32 * (kIdxPitch + kWPitch + kGPitch);
   static constexpr int kVals = 6 + 3 * DT;
   static constexpr int kAcc = (kVals + 3) & ~3;                 // floats per face record
@@ -1761,8 +2096,11 @@ __device__ __forceinline__ void row_pixel(const RowFace<DT>& c, float aw, float 
   }
 }
 
+#ifndef DIBR_ROWS_MINB
+#define DIBR_ROWS_MINB 20
+#endif
 template <int DT>
-__global__ void __launch_bounds__(32) raster_bwd_rows_kernel(const __grid_constant__ RowBwdArgs a) {
+__global__ void __launch_bounds__(32, DIBR_ROWS_MINB) raster_bwd_rows_kernel(const __grid_constant__ RowBwdArgs a) {
   using C = RwCfg<DT>;
   __shared__ __align__(128) unsigned char smem[2 * C::kStage];
   const int lane = threadIdx.x;
@@ -1781,20 +2119,20 @@ __global__ void __launch_bounds__(32) raster_bwd_rows_kernel(const __grid_consta
     unsigned char* base = smem + buf * C::kStage;
     const int x = col0 + s * kRwSlab;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {           // face_idx: 4 chunks per row
-      const int r = (lane >> 2) + 8 * j, ch = lane & 3;
+    for (int j = 0; j < 2; ++j) {           // face_idx: 2 chunks per row
+      const int k = lane + 32 * j, r = k >> 1, ch = k & 1;
       if (row0 + r < a.H)
         cp_async16(base + r * C::kIdxPitch + ch * 16,
                    reinterpret_cast<const char*>(a.idx + pix0 + (int64_t)r * a.W + x) + ch * 16);
     }
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {           // weights: 6 chunks per row
-      const int k = lane + 32 * j, r = k / 6, ch = k - r * 6;
+    for (int j = 0; j < 3; ++j) {           // weights: 3 chunks per row
+      const int k = lane + 32 * j, r = k / 3, ch = k - r * 3;
       if (row0 + r < a.H)
         cp_async16(base + 32 * C::kIdxPitch + r * C::kWPitch + ch * 16,
                    reinterpret_cast<const char*>(a.w + (pix0 + (int64_t)r * a.W + x) * 3) + ch * 16);
     }
-    constexpr int GC = C::kGRow / 16;       // upstream gradient: 2*D chunks per row
+    constexpr int GC = C::kGRow / 16;       // upstream gradient: D chunks per row
 #pragma unroll
     for (int j = 0; j < GC; ++j) {
       const int k = lane + 32 * j, r = k / GC, ch = k - r * GC;
@@ -1823,19 +2161,18 @@ __global__ void __launch_bounds__(32) raster_bwd_rows_kernel(const __grid_consta
     __syncwarp();
     const unsigned char* base = smem + (s & 1) * C::kStage;
     if (row_ok) {
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(base + lane * C::kIdxPitch + half * 32);
+      do {
+        const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(base + lane * C::kIdxPitch);
         const ulonglong2 i01 = ip[0], i23 = ip[1];
         int f[4] = {(int)(long long)i01.x, (int)(long long)i01.y, (int)(long long)i23.x, (int)(long long)i23.y};
         bool any = cur >= 0;
 #pragma unroll
         for (int p = 0; p < 4; ++p) { f[p] = f[p] < 0 ? -1 : f[p]; any = any || f[p] >= 0; }
-        if (!any) continue;
-        const float4* wp = reinterpret_cast<const float4*>(base + 32 * C::kIdxPitch + lane * C::kWPitch + half * 48);
+        if (!any) break;
+        const float4* wp = reinterpret_cast<const float4*>(base + 32 * C::kIdxPitch + lane * C::kWPitch);
         const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2];
         const float wv[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
-        const float4* gp = reinterpret_cast<const float4*>(base + 32 * (C::kIdxPitch + C::kWPitch) + lane * C::kGPitch + half * (16 * DT));
+        const float4* gp = reinterpret_cast<const float4*>(base + 32 * (C::kIdxPitch + C::kWPitch) + lane * C::kGPitch);
         float gv[4 * DT];
 #pragma unroll
         for (int k = 0; k < DT; ++k) { const float4 t = gp[k]; gv[4 * k] = t.x; gv[4 * k + 1] = t.y; gv[4 * k + 2] = t.z; gv[4 * k + 3] = t.w; }
@@ -1852,7 +2189,7 @@ __global__ void __launch_bounds__(32) raster_bwd_rows_kernel(const __grid_consta
           }
           if (cur >= 0) row_pixel<DT>(fc, wv[3 * p], wv[3 * p + 1], wv[3 * p + 2], &gv[DT * p], acc);
         }
-      }
+      } while (false);
     }
     __syncwarp();  // everyone is done with this buffer before slab s+2 lands in it
   }
@@ -1860,28 +2197,33 @@ __global__ void __launch_bounds__(32) raster_bwd_rows_kernel(const __grid_consta
 }
 
 // acc[face][kAcc] -> grad_face_vertices_image (NF,3,2) (= or +=) and grad_face_features (NF,3,D) (=).
+// A CTA moves 256 face records through shared memory so that both the 64-byte records and the
+// 24- / 12*D-byte output rows are read and written as contiguous, fully used lines.
 template <int DT>
 __global__ void __launch_bounds__(256) raster_bwd_finalize_kernel(const float* __restrict__ acc, int64_t NF,
                                                                  float* __restrict__ g_xy, float* __restrict__ g_ff,
                                                                  int accumulate_xy) {
   using C = RwCfg<DT>;
-  const int64_t f = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= NF) return;
-  float v[C::kAcc];
-  const float4* p = reinterpret_cast<const float4*>(acc + f * C::kAcc);
-#pragma unroll
-  for (int i = 0; i < C::kAcc; i += 4) { const float4 t = __ldcs(p + (i >> 2)); v[i] = t.x; v[i + 1] = t.y; v[i + 2] = t.z; v[i + 3] = t.w; }
-  float2* gx = reinterpret_cast<float2*>(g_xy + f * 6);
-  if (accumulate_xy) {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) { const float2 o = gx[j]; gx[j] = make_float2(o.x + v[2 * j], o.y + v[2 * j + 1]); }
-  } else {
-#pragma unroll
-    for (int j = 0; j < 3; ++j) gx[j] = make_float2(v[2 * j], v[2 * j + 1]);
+  constexpr int kFaces = 256;
+  __shared__ __align__(16) float sm[kFaces * C::kAcc];
+  const int64_t f0 = (int64_t)blockIdx.x * kFaces;
+  const int nf = (int)min((int64_t)kFaces, NF - f0);
+  const int tid = threadIdx.x;
+  const float4* src = reinterpret_cast<const float4*>(acc + f0 * C::kAcc);
+  for (int i = tid; i < nf * (C::kAcc / 4); i += 256) reinterpret_cast<float4*>(sm)[i] = __ldcs(src + i);
+  __syncthreads();
+  float2* gx = reinterpret_cast<float2*>(g_xy + f0 * 6);
+  for (int i = tid; i < nf * 3; i += 256) {          // (face, vertex) -> float2
+    const int f = i / 3, v = i - f * 3;
+    float2 o = make_float2(sm[f * C::kAcc + 2 * v], sm[f * C::kAcc + 2 * v + 1]);
+    if (accumulate_xy) { const float2 p = gx[i]; o.x += p.x; o.y += p.y; }
+    gx[i] = o;
   }
-  float* gf = g_ff + f * 3 * DT;
-#pragma unroll
-  for (int j = 0; j < 3 * DT; ++j) gf[j] = v[6 + j];
+  float* gf = g_ff + f0 * 3 * DT;
+  for (int i = tid; i < nf * 3 * DT; i += 256) {
+    const int f = i / (3 * DT), j = i - f * (3 * DT);
+    gf[i] = sm[f * C::kAcc + 6 + j];
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -2085,8 +2427,25 @@ void launch_fwd(const FwdArgs& a0, cudaStream_t st) {
   FwdArgs a = a0;
   a.from_fb = 0;
   {
-    Span sp("dibr_tile_fwd_kernel", st);
-    dibr_tile_fwd_kernel<R, S, K, FT><<<tile_grid(a.s), kThreads, 0, st>>>(a);
+    // S = 2 (32x32 px per CTA, candidates staged once for 4 tiles) when the mesh is sparse enough
+    // for a 32x32 tile's candidates to fit one staging round and the grid still fills the GPU;
+    // dense meshes / small images keep one tile per CTA.
+    const char* force = getenv("DIBR_B200_FWD");   // "old" | "s1" | "s2": A/B switches
+    const int64_t tiles32 = (int64_t)((a.s.W + 31) / 32) * ((a.s.H + 31) / 32);
+    const int64_t faces_per_view = a.s.NF / (a.s.B > 0 ? a.s.B : 1);
+    bool two = R && faces_per_view * 3 / 2 <= 200 * tiles32 && tiles32 * a.s.B >= 2048;
+    if (force && force[0] == 's') two = force[1] == '2';
+    if (force && force[0] == 'o') {
+      Span sp("dibr_tile_fwd_kernel", st);
+      dibr_tile_fwd_kernel<R, S, K, FT><<<tile_grid(a.s), kThreads, 0, st>>>(a);
+    } else if (two) {
+      Span sp("dibr_fwd2_kernel<S=2>", st);
+      const dim3 grid((unsigned)((a.s.ntx[0] + 1) / 2), (unsigned)((a.s.nty[0] + 1) / 2), (unsigned)a.s.B);
+      dibr_fwd2_kernel<R, S, K, FT, 2><<<grid, kThreads, 0, st>>>(a);
+    } else {
+      Span sp("dibr_fwd2_kernel<S=1>", st);
+      dibr_fwd2_kernel<R, S, K, FT, 1><<<tile_grid(a.s), kThreads, 0, st>>>(a);
+    }
   }
   if (S) {
     cudaFuncSetAttribute(soft_tiles_fwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -2305,7 +2664,7 @@ static int backward_impl(int batch, int num_faces, int height, int width, int fe
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
   const bool run_raster = grad_features && feat_dim > 0;
-  // row-walk kernel: fp32 features, D <= 4, rows a multiple of 8 px, a workspace with the face records
+  // row-walk kernel: fp32 features, D <= 4, rows a multiple of 4 px, a workspace with the face records
   float* acc = nullptr;
   if (run_raster && !bf16 && feat_dim <= 4 && (width % kRwSlab) == 0 && NF > 0) {
     const char* force = getenv("DIBR_B200_RASTER_BWD");   // "warp": A/B against the warp-reduction kernel

@@ -1,5 +1,7 @@
-"""Drop-in for ``kaolin.render.mesh``'s DIB-R path (kaolin/render/mesh/__init__.py:1-5)."""
+"""Drop-in for ``kaolin.render.mesh``'s DIB-R path (kaolin/render/mesh/__init__.py:1-5) and the
+steps either side of it (``prepare_vertices``, ``texture_mapping``: kaolin/render/mesh/utils.py)."""
 from .rasterization import rasterize
 from .dibr import dibr_soft_mask, dibr_rasterization
+from .utils import prepare_vertices, texture_mapping
 
-__all__ = ["rasterize", "dibr_soft_mask", "dibr_rasterization"]
+__all__ = ["rasterize", "dibr_soft_mask", "dibr_rasterization", "prepare_vertices", "texture_mapping"]

@@ -46,6 +46,30 @@ def check_tensors(func, named, dtype=torch.float32):
     return dev
 
 
+_warned_fp64 = []
+
+
+def wants_fp64(*tensors):
+    """True when the caller passed float64 geometry/features (the reference dispatches float and
+    double, rasterization_cuda.cu:218/427, dibr_soft_mask_cuda.cu:205/376).  kaolin_b200 has fp32
+    kernels only: float64 inputs are ACCEPTED, computed in float32 and the floating-point
+    outputs / gradients are returned as float64 (through differentiable casts), so a double
+    caller keeps working; results carry fp32 rounding (~1e-7 relative) and face_idx can differ
+    from the reference's double kernels at pixels where an fp32 rounding decides coverage or
+    depth order.  Warns once per process."""
+    hit = any(isinstance(t, torch.Tensor) and t.dtype == torch.float64 for t in tensors)
+    if hit and not _warned_fp64:
+        import warnings
+        _warned_fp64.append(True)
+        warnings.warn("kaolin_b200: float64 inputs are computed in float32 (fp32 kernels only); outputs and "
+                      "gradients are cast back to float64", stacklevel=3)
+    return hit
+
+
+def to_fp32(t):
+    return t.to(torch.float32) if isinstance(t, torch.Tensor) and t.dtype == torch.float64 else t
+
+
 def check_size(func, name, t, shape):
     if tuple(t.shape) != tuple(shape):
         raise RuntimeError(f"{func}: expected {name} of size {list(shape)}, got {list(t.shape)}")

@@ -47,6 +47,9 @@ class DibrSoftMaskB200(Function):
 def dibr_soft_mask(face_vertices_image, selected_face_idx, sigmainv=7000, boxlen=0.02,
                    knum=30, multiplier=1000.):
     r"""Soft mask of DIB-R (see kaolin.render.mesh.dibr_soft_mask, dibr.py:75-117)."""
+    if _host.wants_fp64(face_vertices_image):
+        return dibr_soft_mask(face_vertices_image.float(), selected_face_idx, sigmainv, boxlen, knum,
+                              multiplier).double()
     _host.check_tensors("dibr_soft_mask", [("face_vertices_image", face_vertices_image),
                                            ("selected_face_idx", selected_face_idx)])
     if face_vertices_image.dim() != 4 or tuple(face_vertices_image.shape[2:]) != (3, 2):
@@ -103,6 +106,15 @@ def dibr_rasterization(height, width, face_vertices_z, face_vertices_image, face
     if rast_backend != 'cuda':
         raise ValueError(f'"{rast_backend}" is not a valid backend, '
                          'kaolin_b200 only provides ["cuda"]')
+    flat = list(face_features) if isinstance(face_features, (list, tuple)) else [face_features]
+    if _host.wants_fp64(face_vertices_z, face_vertices_image, face_normals_z, *flat):
+        ff32 = [_host.to_fp32(x) for x in flat]
+        out, soft, face_idx = dibr_rasterization(
+            height, width, _host.to_fp32(face_vertices_z), _host.to_fp32(face_vertices_image),
+            ff32 if isinstance(face_features, (list, tuple)) else ff32[0], _host.to_fp32(face_normals_z),
+            sigmainv, boxlen, knum, multiplier, eps, rast_backend)
+        out = tuple(o.double() for o in out) if isinstance(out, tuple) else out.double()
+        return out, soft.double(), face_idx
     if multiplier is None:
         multiplier = 1000
         soft_multiplier = 1000.          # dibr.py:200

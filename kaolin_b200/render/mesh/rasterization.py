@@ -77,6 +77,15 @@ def rasterize(height, width, face_vertices_z, face_vertices_image, face_features
     if backend != 'cuda':
         raise ValueError(f'"{backend}" is not a valid backend, '
                          'kaolin_b200 only provides ["cuda"]')
+    flat = list(face_features) if isinstance(face_features, (list, tuple)) else [face_features]
+    if _host.wants_fp64(face_vertices_z, face_vertices_image, *flat):
+        # float64 callers: fp32 kernels, differentiable casts both ways (see _host.wants_fp64)
+        ff32 = [_host.to_fp32(x) for x in flat]
+        out, face_idx = rasterize(height, width, _host.to_fp32(face_vertices_z), _host.to_fp32(face_vertices_image),
+                                  ff32 if isinstance(face_features, (list, tuple)) else ff32[0],
+                                  valid_faces, multiplier, eps, backend)
+        out = tuple(o.double() for o in out) if isinstance(out, tuple) else out.double()
+        return out, face_idx
     _face_features = torch.cat(face_features, dim=-1) \
         if isinstance(face_features, (list, tuple)) else face_features
     B, F = _check_inputs("rasterize", face_vertices_z, face_vertices_image, _face_features)

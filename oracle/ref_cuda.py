@@ -32,9 +32,10 @@ def module():
     return _mod
 
 
-def rasterize_forward(height, width, fvz, fvi, ff, valid_faces=None, multiplier=1000, eps=1e-8):
-    """RasterizeCuda.forward -> (interp, face_idx, weights)."""
-    C = module()
+def rasterize_forward(height, width, fvz, fvi, ff, valid_faces=None, multiplier=1000, eps=1e-8, C=None):
+    """RasterizeCuda.forward -> (interp, face_idx, weights).  ``C``: the object playing the role of
+    ``kaolin._C.render.mesh`` (default: the reference's own operators, oracle/_ref)."""
+    C = C or module()
     B, F = fvz.shape[:2]
     D = ff.shape[-1]
     dev = fvz.device
@@ -68,15 +69,15 @@ def rasterize_forward(height, width, fvz, fvi, ff, valid_faces=None, multiplier=
     return interp, face_idx, w
 
 
-def rasterize_backward(grad, interp, face_idx, w, fvi, ff, eps=1e-8):
-    C = module()
+def rasterize_backward(grad, interp, face_idx, w, fvi, ff, eps=1e-8, C=None):
+    C = C or module()
     return C.rasterize_backward_cuda(grad.contiguous(), interp, face_idx, w,
                                      fvi.contiguous(), ff.contiguous(), eps)
 
 
-def soft_mask_forward(fvi, face_idx, sigmainv=7000, boxlen=0.02, knum=30, multiplier=1000.):
+def soft_mask_forward(fvi, face_idx, sigmainv=7000, boxlen=0.02, knum=30, multiplier=1000., C=None):
     """DibrSoftMaskCuda.forward -> (soft, fvi_m, prob, cidx, ctype)."""
-    C = module()
+    C = C or module()
     fvi_m = fvi.contiguous() * multiplier
     pmin = torch.min(fvi_m, dim=-2)[0]
     pmax = torch.max(fvi_m, dim=-2)[0]
@@ -87,23 +88,23 @@ def soft_mask_forward(fvi, face_idx, sigmainv=7000, boxlen=0.02, knum=30, multip
 
 
 def soft_mask_backward(grad_soft, soft, face_idx, prob, cidx, ctype, fvi_m, sigmainv=7000,
-                       multiplier=1000.):
-    C = module()
+                       multiplier=1000., C=None):
+    C = C or module()
     return C.dibr_soft_mask_backward_cuda(grad_soft.contiguous(), soft, face_idx, prob, cidx,
                                           ctype, fvi_m, sigmainv, multiplier)
 
 
 def dibr_forward_backward(height, width, fvz, fvi, ff, fnz, g_feat, g_soft, sigmainv=7000,
-                          boxlen=0.02, knum=30, multiplier=None, eps=None):
+                          boxlen=0.02, knum=30, multiplier=None, eps=None, C=None):
     """dibr_rasterization forward + both backward branches (summed as autograd does)."""
     m = 1000 if multiplier is None else multiplier
     e = 1e-8 if eps is None else eps
-    interp, face_idx, w = rasterize_forward(height, width, fvz, fvi, ff, fnz >= 0., m, e)
+    interp, face_idx, w = rasterize_forward(height, width, fvz, fvi, ff, fnz >= 0., m, e, C=C)
     _m = 1000. if multiplier is None else multiplier
-    soft, fvi_m, prob, cidx, ctype = soft_mask_forward(fvi, face_idx, sigmainv, boxlen, knum, _m)
+    soft, fvi_m, prob, cidx, ctype = soft_mask_forward(fvi, face_idx, sigmainv, boxlen, knum, _m, C=C)
     out = {"features": interp, "face_idx": face_idx, "weights": w, "soft_mask": soft}
     if g_feat is not None:
-        gxy_r, gff = rasterize_backward(g_feat, interp, face_idx, w, fvi, ff, e)
-        gxy_s = soft_mask_backward(g_soft, soft, face_idx, prob, cidx, ctype, fvi_m, sigmainv, _m)
+        gxy_r, gff = rasterize_backward(g_feat, interp, face_idx, w, fvi, ff, e, C=C)
+        gxy_s = soft_mask_backward(g_soft, soft, face_idx, prob, cidx, ctype, fvi_m, sigmainv, _m, C=C)
         out.update(grad_fvi=gxy_r + gxy_s, grad_ff=gff, grad_fvi_raster=gxy_r, grad_fvi_soft=gxy_s)
     return out
