@@ -206,6 +206,66 @@ int dibr_b200_soft_mask_backward(
     float sigmainv, float multiplier, float* grad_face_vertices_image,
     dibr_b200_stream_t stream);
 
+/* =========================================================================
+ * The steps either side of the rasterizer in every DIB-R caller;
+ * kaolin_b200/csrc/mesh_pipeline.cu.  The reference has no native interface for them: they
+ * are chains of PyTorch ops (cited per entry point); the signatures below are what a
+ * binding for a fused version would take.  No workspace; asynchronous on `stream`.
+ * ========================================================================= */
+
+/*
+ * prepare_vertices (kaolin/render/mesh/utils.py:129-175): camera transform
+ * (camera/legacy.py:22-37 with camera_rot (B,3,3) + camera_trans (B,3), or
+ * [p,1] @ camera_transform (B,4,3); pass exactly one of the two), perspective divide
+ * (camera/legacy.py:120-138; camera_proj_host = 3 floats on the HOST), gather by `faces`
+ * (F,3) i64 (ops/mesh/mesh.py:54-76) and unit face normals (ops/mesh/trianglemesh.py:314-338).
+ * Outputs: face_vertices_camera (B,F,3,3), face_vertices_image (B,F,3,2), face_normals (B,F,3).
+ */
+int dibr_b200_prepare_vertices_forward(
+    int batch, int num_vertices, int num_faces, const float* vertices, const int64_t* faces,
+    const float* camera_transform, const float* camera_rot, const float* camera_trans,
+    const float* camera_proj_host, float* face_vertices_camera, float* face_vertices_image,
+    float* face_normals, dibr_b200_stream_t stream);
+
+/* Gradient wrt the CAMERA-SPACE vertices (B,V,3) (zeroed inside, scattered with float
+ * atomics); any of the three upstream gradients may be NULL.  The linear map back to
+ * world-space vertices / camera parameters is a (B,V,3)x(3,3) product left to the caller. */
+int dibr_b200_prepare_vertices_backward(
+    int batch, int num_vertices, int num_faces, const float* vertices, const int64_t* faces,
+    const float* camera_transform, const float* camera_rot, const float* camera_trans,
+    const float* camera_proj_host, const float* grad_face_vertices_camera,
+    const float* grad_face_vertices_image, const float* grad_face_normals,
+    float* grad_vertices_camera, dibr_b200_stream_t stream);
+
+/*
+ * texture_mapping (kaolin/render/mesh/utils.py:22-79): texture_coordinates (B,N,2) in [0,1]
+ * (OpenGL convention), texture_maps (B,C,Ht,Wt); clamp, y flip,
+ * grid_sample(align_corners=False, padding_mode='border'), mode nearest (1) or bilinear (0).
+ * out (B,N,C).  Backward: grad_texture_maps (B,C,Ht,Wt) (zeroed inside) and/or
+ * grad_texture_coordinates (B,N,2); either may be NULL.
+ */
+int dibr_b200_texture_mapping_forward(
+    int batch, int64_t num_points, int channels, int tex_height, int tex_width,
+    const float* texture_coordinates, const float* texture_maps, int nearest, float* out,
+    dibr_b200_stream_t stream);
+int dibr_b200_texture_mapping_backward(
+    int batch, int64_t num_points, int channels, int tex_height, int tex_width,
+    const float* texture_coordinates, const float* texture_maps, int nearest,
+    const float* grad_out, float* grad_texture_maps, float* grad_texture_coordinates,
+    dibr_b200_stream_t stream);
+
+/*
+ * mask_iou (kaolin/metrics/render.py:18-41): loss = 1 - mean_b(sum(l*r) / (sum(l+r-l*r) + 1e-10)).
+ * sums (B,2) f32 scratch/output {sum(l*r), sum(l+r-l*r)} kept for the backward; loss: 1 f32.
+ */
+int dibr_b200_mask_iou_forward(
+    int batch, int64_t pixels_per_view, const float* lhs_mask, const float* rhs_mask,
+    float* sums, float* loss, dibr_b200_stream_t stream);
+int dibr_b200_mask_iou_backward(
+    int batch, int64_t pixels_per_view, const float* lhs_mask, const float* rhs_mask,
+    const float* sums, const float* grad_loss, float* grad_lhs, float* grad_rhs,
+    dibr_b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

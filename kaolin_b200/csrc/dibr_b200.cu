@@ -1364,6 +1364,48 @@ __global__ void __launch_bounds__(kThreads, DIBR_FWD2_MINB) dibr_fwd2_kernel(con
 
   bool staged = false;
 
+  // ---- CTA tiles that no valid face touches (40 % of them on the benchmark scene): the outputs are
+  // constants, written as full 16-byte vectors row by row (9 stores per thread instead of 32)
+  if (RASTER && !KLISTS && total == 0 && cta_x0 + kSide <= s.W && cta_y0 + kSide <= s.H && (s.W & 3) == 0 &&
+      std::is_same<FT, float>::value && a.D == 3) {
+    const int64_t pix_row0 = ((int64_t)b * s.H + cta_y0) * s.W + cta_x0;
+    const int4 neg = make_int4(-1, -1, -1, -1);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    constexpr int kIdxC = kSide * 8 / 16, kWC = kSide * 12 / 16, kSC = kSide * 4 / 16;   // 16-byte chunks per row
+    for (int c = tid; c < kSide * kIdxC; c += kThreads) {
+      const int r = c / kIdxC, ch = c - r * kIdxC;
+      reinterpret_cast<int4*>(a.idx + pix_row0 + (int64_t)r * s.W)[ch] = neg;
+    }
+    for (int c = tid; c < kSide * kWC; c += kThreads) {
+      const int r = c / kWC, ch = c - r * kWC;
+      reinterpret_cast<float4*>(a.out_w + (pix_row0 + (int64_t)r * s.W) * 3)[ch] = zero;
+      reinterpret_cast<float4*>(static_cast<float*>(a.out_feat) + (pix_row0 + (int64_t)r * s.W) * 3)[ch] = zero;
+    }
+    if (SOFT) {
+      for (int c = tid; c < kSide * kSC; c += kThreads) {
+        const int r = c / kSC, ch = c - r * kSC;
+        reinterpret_cast<float4*>(a.out_soft + pix_row0 + (int64_t)r * s.W)[ch] = zero;   // uncovered, no neighbour yet
+      }
+      if (tid < kSubs) {   // every pixel is uncovered: file the sub-tiles an enlarged face can reach
+        const int tx = ctx0 + tid % S, ty = cty0 + tid / S;
+        const int nlarge = ((__ldg(s.tile_cnt + ((size_t)b * s.nty[0] + ty) * ((s.ntx[0] + 31) >> 5) + (tx >> 5)) >> (tx & 31)) & 1) +
+                           __ldg(s.view_flag + b);
+        if (nlarge > 0) {
+          int* rec = s.band_list + (size_t)atomicAdd(s.band_ctr, 1) * kBandRec;
+          const int4* ebase = s.entries + (size_t)4 * s.NF + 4 * fbase;
+          rec[0] = (b * s.nty[0] + ty) * s.ntx[0] + tx;
+          for (int q = 0; q < kThreads / 32; ++q) rec[1 + q] = -1;
+          for (int l = 0; l < kMaxLevels; ++l) {
+            const BinRef br = l == 0 ? sm.bin0[1][tid] : sm.bin[1][l];
+            rec[9 + 2 * l] = br.n > 0 ? (int)(br.ptr - ebase) : 0;
+            rec[10 + 2 * l] = br.n;
+          }
+        }
+      }
+    }
+    return;
+  }
+
   for (int sub = 0; sub < kSubs; ++sub) {
     const int sx = sub % S, sy = sub / S;
     const int tx = ctx0 + sx, ty = cty0 + sy;
@@ -1391,7 +1433,10 @@ __global__ void __launch_bounds__(kThreads, DIBR_FWD2_MINB) dibr_fwd2_kernel(con
               if (k + 1 < nrounds) issue(k + 1);   // its buffer was released by the barrier ending round k-1
             }
             const int buf = waited & 1;
-            mbar_wait(&sm.bar[buf], (uint32_t)((waited >> 1) & 1));
+            // only the warps that read the landing buffer poll the mbarrier; the others go
+            // straight to the CTA barrier below and sleep there (256 polling threads cost 5 % of
+            // the kernel's instructions in the first version)
+            if ((tid & ~31) < cnt) mbar_wait(&sm.bar[buf], (uint32_t)((waited >> 1) & 1));
             ++waited;
             uint32_t cm = 0, rm = 0;
             if (tid < cnt) {
@@ -1843,6 +1888,74 @@ __global__ void __launch_bounds__(kThreads) soft_bwd_dense_kernel(const __grid_c
   }
 }
 
+// Dense soft-mask backward, RUN variant: the hits of a tile lie face-major in its cache block, so
+// a thread that takes 8 CONSECUTIVE hits (two LDG.128 per array, 32 bytes per lane, 1 KB per warp
+// request) sees one or two faces.  It sums the six partials of a face in registers and flushes
+// them with three RED.v2 when the face changes - no match/shuffle reduction (30 SHFL per warp at
+// 1 SHFL per clock per SM in the kernel above) and one face-vertex load per run instead of per hit.
+constexpr int kRunHits = 8;
+
+__global__ void __launch_bounds__(kThreads) soft_bwd_runs_kernel(const __grid_constant__ SoftBwdArgs a) {
+  const Scene& s = a.s;
+  const int used = min(*s.pool_ctr, s.pool_tiles);
+  if ((int)blockIdx.x >= used) return;
+  const int4 h = s.pool_hdr[blockIdx.x];  // b, tx, ty, hits
+  const size_t E = (size_t)256 * s.pool_K;
+  const uint32_t* blk = s.pool_data + (size_t)blockIdx.x * 3 * E;
+  const int64_t fbase = view_fbase(s, h.x);
+  const float inv_m = 1.0f / s.multiplier;
+  const int64_t pix_tile = ((int64_t)h.x * s.H + (int64_t)h.z * kTile) * s.W + h.y * kTile;
+  for (int start = threadIdx.x * kRunHits; start < h.w; start += kThreads * kRunHits) {
+    const int n = min(kRunHits, h.w - start);
+    uint32_t face[kRunHits], prob[kRunHits], meta[kRunHits];
+    {
+      const uint4* pf = reinterpret_cast<const uint4*>(blk + start);
+      const uint4* pp = reinterpret_cast<const uint4*>(blk + E + start);
+      const uint4* pm = reinterpret_cast<const uint4*>(blk + 2 * E + start);
+      // the block is sized 256*K entries: reading the (unused) tail of the last group of 8 stays inside it
+      const uint4 f0 = __ldcs(pf), f1 = __ldcs(pf + 1), p0 = __ldcs(pp), p1 = __ldcs(pp + 1);
+      const uint4 m0 = __ldcs(pm), m1 = __ldcs(pm + 1);
+      face[0] = f0.x; face[1] = f0.y; face[2] = f0.z; face[3] = f0.w; face[4] = f1.x; face[5] = f1.y; face[6] = f1.z; face[7] = f1.w;
+      prob[0] = p0.x; prob[1] = p0.y; prob[2] = p0.z; prob[3] = p0.w; prob[4] = p1.x; prob[5] = p1.y; prob[6] = p1.z; prob[7] = p1.w;
+      meta[0] = m0.x; meta[1] = m0.y; meta[2] = m0.z; meta[3] = m0.w; meta[4] = m1.x; meta[5] = m1.y; meta[6] = m1.z; meta[7] = m1.w;
+    }
+    int cur = -1;
+    float v[6], acc[6];
+#pragma unroll
+    for (int j = 0; j < kRunHits; ++j) {
+      if (j < n) {
+        const int f = (int)face[j];
+        if (f != cur) {
+          if (cur >= 0) {
+            float2* gx = reinterpret_cast<float2*>(a.grad_xy + (fbase + cur) * 6);
+            if (acc[0] != 0.f || acc[1] != 0.f) atomicAdd(gx, make_float2(acc[0], acc[1]));
+            if (acc[2] != 0.f || acc[3] != 0.f) atomicAdd(gx + 1, make_float2(acc[2], acc[3]));
+            if (acc[4] != 0.f || acc[5] != 0.f) atomicAdd(gx + 2, make_float2(acc[4], acc[5]));
+          }
+          cur = f;
+          load_xy(s, fbase + f, v);
+#pragma unroll
+          for (int q = 0; q < 6; ++q) acc[q] = 0.f;
+        }
+        const int lx = (int)(meta[j] & 15u), ly = (int)((meta[j] >> 4) & 15u);
+        const int64_t pix = pix_tile + (int64_t)ly * s.W + lx;
+        float g[6];
+        soft_backward_terms_fast(pix_x(s.grid, h.y * kTile + lx), pix_y(s.grid, h.z * kTile + ly), v,
+                                 (int)(meta[j] >> 8) - 1, __uint_as_float(prob[j]), __ldg(a.soft + pix),
+                                 __ldg(a.grad_soft + pix), a.sigmainv, inv_m, g);
+#pragma unroll
+        for (int q = 0; q < 6; ++q) acc[q] += g[q];
+      }
+    }
+    if (cur >= 0) {
+      float2* gx = reinterpret_cast<float2*>(a.grad_xy + (fbase + cur) * 6);
+      if (acc[0] != 0.f || acc[1] != 0.f) atomicAdd(gx, make_float2(acc[0], acc[1]));
+      if (acc[2] != 0.f || acc[3] != 0.f) atomicAdd(gx + 1, make_float2(acc[2], acc[3]));
+      if (acc[4] != 0.f || acc[5] != 0.f) atomicAdd(gx + 2, make_float2(acc[4], acc[5]));
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------
 // Rasterize backward: pixel-parallel; lanes of a warp (an 8x4 pixel block) that
 // hit the same face are summed with a segmented shuffle reduction, so a face
@@ -2026,7 +2139,8 @@ struct RowBwdArgs {
   int B, H, W, F, strip, jobs_x, jobs_y;
   const float* grad_feat; const int64_t* idx; const float* w; const float* xy; const float* feat;
   float eps;
-  float* acc;  // [B*F][RwCfg<D>::kAcc], zeroed
+  float* acc;    // [B*F][RwCfg<D>::kAcc], zeroed
+  int* job_ctr;  // [1] zeroed (lives right behind the records)
 };
 
 template <int DT>
@@ -2104,7 +2218,15 @@ __global__ void __launch_bounds__(32, DIBR_ROWS_MINB) raster_bwd_rows_kernel(con
   using C = RwCfg<DT>;
   __shared__ __align__(128) unsigned char smem[2 * C::kStage];
   const int lane = threadIdx.x;
-  int job = blockIdx.x;
+  // persistent single-warp CTAs pull (view, 32-row band, column strip) jobs from a counter: the
+  // jobs differ by 10x in cost (background vs dense mesh), so a static grid ends with a
+  // ragged tail of half-empty SMs
+  const int total_jobs = a.jobs_x * a.jobs_y * a.B;
+  for (;;) {
+  int job = 0;
+  if (lane == 0) job = atomicAdd(a.job_ctr, 1);
+  job = __shfl_sync(kFull, job, 0);
+  if (job >= total_jobs) break;
   const int jx = job % a.jobs_x; job /= a.jobs_x;
   const int jy = job % a.jobs_y;
   const int b = job / a.jobs_y;
@@ -2194,6 +2316,8 @@ __global__ void __launch_bounds__(32, DIBR_ROWS_MINB) raster_bwd_rows_kernel(con
     __syncwarp();  // everyone is done with this buffer before slab s+2 lands in it
   }
   if (cur >= 0) flush();
+  __syncwarp();
+  }  // job loop
 }
 
 // acc[face][kAcc] -> grad_face_vertices_image (NF,3,2) (= or +=) and grad_face_features (NF,3,D) (=).
@@ -2293,7 +2417,7 @@ Layout layout_for(int B, int64_t NF, int H, int W) {
   L.off = align_up((size_t)2 * B * bins_per_view(H, W) * sizeof(int), 256);
   L.mode = align_up(tiles * sizeof(int), 256) + align_up(tiles * kBandRec * sizeof(int), 256);
   L.ent = align_up((size_t)2 * 4 * (size_t)(NF > 0 ? NF : 1) * sizeof(int4), 256);
-  L.acc = align_up((size_t)(NF > 0 ? NF : 1) * kAccMax * sizeof(float), 256);  // rasterize-backward face records
+  L.acc = align_up((size_t)(NF > 0 ? NF : 1) * kAccMax * sizeof(float) + 16, 256);  // rasterize-backward face records + job counter
   L.base = L.cnt + L.off + L.mode + L.ent + L.acc + 256;
   return L;
 }
@@ -2435,7 +2559,10 @@ void launch_fwd(const FwdArgs& a0, cudaStream_t st) {
     const int64_t faces_per_view = a.s.NF / (a.s.B > 0 ? a.s.B : 1);
     bool two = R && faces_per_view * 3 / 2 <= 200 * tiles32 && tiles32 * a.s.B >= 2048;
     if (force && force[0] == 's') two = force[1] == '2';
-    if (force && force[0] == 'o') {
+    const bool v2_single = force && force[0] == 's' && force[1] == '1';
+    if ((force && force[0] == 'o') || (!two && !v2_single)) {
+      // one 16x16 tile per CTA: dense meshes (hundreds of candidates per tile) and small images;
+      // measured faster there than the v2 kernel with S = 1 (0.90 vs 1.17 ms on the benchmark mesh)
       Span sp("dibr_tile_fwd_kernel", st);
       dibr_tile_fwd_kernel<R, S, K, FT><<<tile_grid(a.s), kThreads, 0, st>>>(a);
     } else if (two) {
@@ -2496,12 +2623,29 @@ float* acc_region(void* ws, size_t ws_bytes, int B, int64_t NF, int H, int W) {
 }
 
 template <int DT>
-int launch_rows_t(const RowBwdArgs& a, int64_t NF, float* g_xy, float* g_ff, int accumulate_xy, cudaStream_t st) {
-  cudaError_t e = cudaMemsetAsync(a.acc, 0, (size_t)NF * RwCfg<DT>::kAcc * sizeof(float), st);
+int launch_rows_t(const RowBwdArgs& a0, int64_t NF, float* g_xy, float* g_ff, int accumulate_xy, cudaStream_t st) {
+  RowBwdArgs a = a0;
+  a.job_ctr = reinterpret_cast<int*>(a.acc + (size_t)NF * RwCfg<DT>::kAcc);   // kAcc <= 16 < kAccMax: room behind the records
+  cudaError_t e = cudaMemsetAsync(a.acc, 0, (size_t)NF * RwCfg<DT>::kAcc * sizeof(float) + sizeof(int), st);
   if (e != cudaSuccess) return (int)e;
   {
     Span sp("raster_bwd_rows_kernel", st);
-    raster_bwd_rows_kernel<DT><<<(unsigned)(a.jobs_x * a.jobs_y * a.B), 32, 0, st>>>(a);
+    // resident single-warp CTAs per device: a property of (device, kernel), cached after the first
+    // query (idempotent writes of the same value: safe from any thread)
+    static int slots_of[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    int slots = slots_of[dev & 63];
+    if (slots == 0) {
+      int sms = 148, per_sm = 16;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_bwd_rows_kernel<DT>, 32, 0) != cudaSuccess || per_sm < 1)
+        per_sm = 16;
+      slots = sms * per_sm;
+      slots_of[dev & 63] = slots;
+    }
+    const int64_t jobs = (int64_t)a.jobs_x * a.jobs_y * a.B;
+    raster_bwd_rows_kernel<DT><<<(unsigned)(jobs < slots ? jobs : slots), 32, 0, st>>>(a);
   }
   {
     Span sp("raster_bwd_finalize_kernel", st);
@@ -2518,7 +2662,8 @@ int launch_raster_bwd_rows(const RasterBwdArgs& r, float* acc, int accumulate_xy
   a.grad_feat = static_cast<const float*>(r.grad_feat); a.idx = r.idx; a.w = r.w; a.xy = r.xy;
   a.feat = static_cast<const float*>(r.feat); a.eps = r.eps; a.acc = acc;
   a.jobs_y = (r.H + 31) / 32;
-  int strip = 128;
+  int strip = 64;
+  if (const char* fs = getenv("DIBR_B200_ROWS_STRIP")) { const int v = atoi(fs); if (v >= kRwSlab && v % kRwSlab == 0) strip = v; }
   while (strip > kRwSlab && (int64_t)r.B * a.jobs_y * ((r.W + strip - 1) / strip) < 8192) strip >>= 1;
   a.strip = strip;
   a.jobs_x = (r.W + strip - 1) / strip;
@@ -2714,8 +2859,14 @@ static int backward_impl(int batch, int num_faces, int height, int width, int fe
       // forward left the bins, the hit cache and the list of tiles it could not cache
       a.from_list = 1;
       if (s.pool_tiles > 0) {
-        Span sp("soft_bwd_dense_kernel", st);
-        soft_bwd_dense_kernel<<<(unsigned)s.pool_tiles, kThreads, 0, st>>>(a);
+        const char* force = getenv("DIBR_B200_SOFT_BWD");   // "dense": A/B against the shuffle-reduction kernel
+        if (force && force[0] == 'd') {
+          Span sp("soft_bwd_dense_kernel", st);
+          soft_bwd_dense_kernel<<<(unsigned)s.pool_tiles, kThreads, 0, st>>>(a);
+        } else {
+          Span sp("soft_bwd_runs_kernel", st);
+          soft_bwd_runs_kernel<<<(unsigned)s.pool_tiles, kThreads, 0, st>>>(a);
+        }
       }
       Span sp("dibr_tile_soft_bwd_kernel<leftovers>", st);
       dibr_tile_soft_bwd_kernel<<<persistent, kThreads, 0, st>>>(a);

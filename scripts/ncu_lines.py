@@ -42,16 +42,11 @@ def main():
     funcs = re.split(r"\n//-+ \.text\.", dis)
     pick = None
     want = re.sub(r"[^A-Za-z0-9_]", "", kname.split("(")[0].split("::")[-1].split("<")[0])
-    targs = re.findall(r"\((?:bool|int)\)(\d+)", kname)
+    targs = re.findall(r"\((bool|int)\)(\d+)", kname)
+    pat = ".*".join(f"L{'b' if t == 'bool' else 'i'}{v}E" for t, v in targs)
     for f in funcs[1:]:
         name = f.split(" ", 1)[0]
-        if want in name:
-            if targs:
-                tag = "IL" + "EL".join(("b" if "bool" in kname else "i") + t for t in targs)
-                # crude: all template values must appear in order
-                enc = "".join(f"L{'b' if '(bool)' in kname else 'i'}{t}E" for t in targs)
-                if enc not in name:
-                    continue
+        if want in name and (not targs or re.search(pat, name)):
             pick = f
             break
     if pick is None:

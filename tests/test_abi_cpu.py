@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for name in declared:
         assert hasattr(lib, name), name
     assert set(_lib.SIGNATURES) == declared
-    assert lib.dibr_b200_version() >= 100
+    assert lib.dibr_b200_version() >= 200
 
 
 def test_header_cites_reference_interfaces():

@@ -596,8 +596,11 @@ def test_errors_like_reference():
         dibr_rasterization(8, 8, T(fvz), T(fvi), T(ff), T(fnz), rast_backend="nvdiffrast_fwd")
     with pytest.raises(RuntimeError):   # CPU tensors: no CPU path (rasterization.cpp:95-102)
         rasterize(8, 8, torch.from_numpy(fvz), torch.from_numpy(fvi), torch.from_numpy(ff))
-    with pytest.raises(RuntimeError):   # double not implemented
-        rasterize(8, 8, T(fvz).double(), T(fvi).double(), T(ff).double())
+    # float64 callers are served (fp32 kernels, outputs cast back): tests/test_reference_wrappers.py
+    out64, _ = rasterize(8, 8, T(fvz).double(), T(fvi).double(), T(ff).double())
+    assert out64.dtype == torch.float64
+    with pytest.raises(RuntimeError):   # half precision geometry is not a reference dtype either
+        rasterize(8, 8, T(fvz).half(), T(fvi).half(), T(ff).half())
     with pytest.raises(RuntimeError):   # non-contiguous operator argument (checkAllContiguous)
         b200_C.render.mesh.rasterize_backward_cuda(
             torch.zeros(1, 8, 8, 2, device=DEV).transpose(1, 2), torch.zeros(1, 8, 8, 2, device=DEV),
