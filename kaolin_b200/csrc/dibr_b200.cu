@@ -1632,6 +1632,7 @@ __global__ void __launch_bounds__(kThreads, 4) soft_tiles_fwd_kernel(const __gri
 //                      (a tile's pairs are all evaluated by the CTA that folds them).
 // Tiles that do not fit the cache go to fb_list and take the single-kernel path.
 constexpr int kEnumK = 32;
+constexpr int kRunHits = 8;   // consecutive cached pairs per thread in the run kernels
 
 struct EnumSmem {
   unsigned long long list[kSoftCap];
@@ -1648,7 +1649,10 @@ struct EnumSmem {
   int nsoft, nent, pool_slot, npairs;
 };
 
-__global__ void __launch_bounds__(kThreads) soft_enum_kernel(const __grid_constant__ FwdArgs a) {
+#ifndef DIBR_ENUM_MINB
+#define DIBR_ENUM_MINB 6   /* measured: 80 registers / 3 CTAs per SM 0.436 ms, 48 / 5: 0.388, 40 / 6: 0.374 */
+#endif
+__global__ void __launch_bounds__(kThreads, DIBR_ENUM_MINB) soft_enum_kernel(const __grid_constant__ FwdArgs a) {
   __shared__ __align__(128) EnumSmem sm;
   const Scene& s = a.s;
   const int K = a.K;
@@ -1893,9 +1897,10 @@ __global__ void __launch_bounds__(kThreads) soft_bwd_dense_kernel(const __grid_c
 // request) sees one or two faces.  It sums the six partials of a face in registers and flushes
 // them with three RED.v2 when the face changes - no match/shuffle reduction (30 SHFL per warp at
 // 1 SHFL per clock per SM in the kernel above) and one face-vertex load per run instead of per hit.
-constexpr int kRunHits = 8;
-
-__global__ void __launch_bounds__(kThreads) soft_bwd_runs_kernel(const __grid_constant__ SoftBwdArgs a) {
+#ifndef DIBR_SBWD_MINB
+#define DIBR_SBWD_MINB 3
+#endif
+__global__ void __launch_bounds__(kThreads, DIBR_SBWD_MINB) soft_bwd_runs_kernel(const __grid_constant__ SoftBwdArgs a) {
   const Scene& s = a.s;
   const int used = min(*s.pool_ctr, s.pool_tiles);
   if ((int)blockIdx.x >= used) return;
@@ -2662,7 +2667,7 @@ int launch_raster_bwd_rows(const RasterBwdArgs& r, float* acc, int accumulate_xy
   a.grad_feat = static_cast<const float*>(r.grad_feat); a.idx = r.idx; a.w = r.w; a.xy = r.xy;
   a.feat = static_cast<const float*>(r.feat); a.eps = r.eps; a.acc = acc;
   a.jobs_y = (r.H + 31) / 32;
-  int strip = 64;
+  int strip = 32;   // measured on the benchmark scene: 128 -> 0.494, 64 -> 0.526, 32 -> 0.542 of HBM peak
   if (const char* fs = getenv("DIBR_B200_ROWS_STRIP")) { const int v = atoi(fs); if (v >= kRwSlab && v % kRwSlab == 0) strip = v; }
   while (strip > kRwSlab && (int64_t)r.B * a.jobs_y * ((r.W + strip - 1) / strip) < 8192) strip >>= 1;
   a.strip = strip;
