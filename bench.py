@@ -586,10 +586,12 @@ def run_ours(args):
         "bin_faces_kernel<count>": NF_ * 28,                        # xy + validity
         "bin_faces_kernel<fill>": NF_ * (28 + 2 * 16),              # + one bin entry per set
         "dibr_tile_fwd_kernel": A["fwd"],                           # all per-pixel outputs + face reads
+        "dibr_fwd2_kernel<S=2>": A["fwd"], "dibr_fwd2_kernel<S=1>": A["fwd"],
         "raster_bwd_rows_kernel": P_ * (D * sF + 8 + 12) + NF_ * (24 + 3 * D * sF),
         "raster_bwd_finalize_kernel": NF_ * (24 + 3 * D * 4),
         "raster_bwd_kernel": A["bwd_raster"],
         "soft_bwd_dense_kernel": band_px * 16 + NF_ * 24,           # soft, grad, idx of band pixels + grad_xy
+        "soft_bwd_runs_kernel": band_px * 16 + NF_ * 24,
     }
     total_kernel_ms = sum(statistics.mean(v) for v in kernel_ms.values()) or 1.0
     kernels = []

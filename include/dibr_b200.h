@@ -266,6 +266,38 @@ int dibr_b200_mask_iou_backward(
     const float* sums, const float* grad_loss, float* grad_lhs, float* grad_rhs,
     dibr_b200_stream_t stream);
 
+/*
+ * DefTet volumetric renderer operators (kaolin_b200/csrc/deftet.cu).
+ * Operator: kaolin::deftet_sparse_render_forward_cuda (kaolin/csrc/render/mesh/deftet.h,
+ * deftet.cpp:48-113, kernel deftet_cuda.cu:31-194; registered at bindings.cpp next to the four
+ * DIB-R operators).  For every query point the first `knum` faces IN INDEX ORDER whose half-open
+ * bbox holds the point, whose eps-normalised barycentric weights are all >= 0 and whose
+ * interpolated depth lies in [render_ranges[...,0], render_ranges[...,1]).
+ *  face_vertices_z (B,F,3), face_vertices_image (B,F,3,2), face_bboxes (B,F,4) [xmin,ymin,xmax,ymax],
+ *  pixel_coords (B,P,2), render_ranges (B,P,2)  f32
+ *  outputs (B,P,K): face_idx i64 (-1 padded), pixel_depth f32 (-inf padded), w0, w1 f32 (0 padded),
+ *  fully written.  workspace >= dibr_b200_deftet_workspace_bytes(batch, num_faces).
+ */
+size_t dibr_b200_deftet_workspace_bytes(int batch, int num_faces);
+int dibr_b200_deftet_sparse_render_forward(
+    int batch, int num_faces, int num_pixels, int knum,
+    const float* face_vertices_z, const float* face_vertices_image, const float* face_bboxes,
+    const float* pixel_coords, const float* render_ranges, float eps,
+    int64_t* face_idx, float* pixel_depth, float* w0, float* w1,
+    void* workspace, size_t workspace_bytes, dibr_b200_stream_t stream);
+
+/*
+ * Operator: kaolin::deftet_sparse_render_backward_cuda (deftet.cpp:115-170, kernel
+ * deftet_cuda.cu:238-430).  grad_interpolated_features (B,P,K,D), face_idx (B,P,K) i64,
+ * weights (B,P,K,3), face_vertices_image (B,F,3,2), face_features (B,F,3,D);
+ * outputs grad_face_vertices_image (B,F,3,2), grad_face_features (B,F,3,D), zeroed inside.
+ */
+int dibr_b200_deftet_sparse_render_backward(
+    int batch, int num_faces, int num_pixels, int knum, int feat_dim,
+    const float* grad_interpolated_features, const int64_t* face_idx, const float* weights,
+    const float* face_vertices_image, const float* face_features, float eps,
+    float* grad_face_vertices_image, float* grad_face_features, dibr_b200_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -195,10 +195,66 @@ def dibr_soft_mask_backward_cuda(grad_soft_mask, soft_mask, selected_face_idx, c
     return g
 
 
+@_fp64_via_fp32
+def deftet_sparse_render_forward_cuda(face_vertices_z, face_vertices_image, face_bboxes, pixel_coords,
+                                      pixel_depth_ranges, knum, eps):
+    """deftet.cpp:48-113 -> [selected_face_idx, pixel_depths, w0_arr, w1_arr], each (B, P, knum)."""
+    fn = "deftet_sparse_render_forward_cuda"
+    dev = _check_all(fn, [("face_vertices_z", face_vertices_z), ("face_vertices_image", face_vertices_image),
+                          ("face_bboxes", face_bboxes), ("pixel_coords", pixel_coords),
+                          ("pixel_depth_ranges", pixel_depth_ranges)])
+    B, F = face_vertices_z.shape[0], face_vertices_z.shape[1]
+    P = pixel_coords.shape[1]
+    _check_size(fn, "face_vertices_z", face_vertices_z, (B, F, 3))
+    _check_size(fn, "face_vertices_image", face_vertices_image, (B, F, 3, 2))
+    _check_size(fn, "face_bboxes", face_bboxes, (B, F, 4))
+    _check_size(fn, "pixel_coords", pixel_coords, (B, P, 2))
+    _check_size(fn, "pixel_depth_ranges", pixel_depth_ranges, (B, P, 2))
+    idx = torch.empty((B, P, knum), dtype=torch.int64, device=dev)
+    depth = torch.empty((B, P, knum), dtype=torch.float32, device=dev)
+    w0 = torch.empty((B, P, knum), dtype=torch.float32, device=dev)
+    w1 = torch.empty((B, P, knum), dtype=torch.float32, device=dev)
+    n = _lib.lib().dibr_b200_deftet_workspace_bytes(B, F)
+    ws = torch.empty(max(n, 1), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().dibr_b200_deftet_sparse_render_forward(
+            B, F, P, int(knum), _ptr(face_vertices_z), _ptr(face_vertices_image), _ptr(face_bboxes),
+            _ptr(pixel_coords), _ptr(pixel_depth_ranges), float(eps), _ptr(idx), _ptr(depth), _ptr(w0), _ptr(w1),
+            _ptr(ws), ws.numel(), _stream(dev))
+    _lib.check(st, fn)
+    return [idx, depth, w0, w1]
+
+
+@_fp64_via_fp32
+def deftet_sparse_render_backward_cuda(grad_interpolated_features, face_idx, weights, face_vertices_image,
+                                       face_features, eps):
+    """deftet.cpp:115-170 -> [grad_face_vertices_image, grad_face_features]."""
+    fn = "deftet_sparse_render_backward_cuda"
+    dev = _check_all(fn, [("grad_interpolated_features", grad_interpolated_features), ("face_idx", face_idx),
+                          ("weights", weights), ("face_vertices_image", face_vertices_image),
+                          ("face_features", face_features)])
+    B, P, K, D = grad_interpolated_features.shape
+    F = face_vertices_image.shape[1]
+    _check_size(fn, "face_idx", face_idx, (B, P, K))
+    _check_size(fn, "weights", weights, (B, P, K, 3))
+    _check_size(fn, "face_vertices_image", face_vertices_image, (B, F, 3, 2))
+    _check_size(fn, "face_features", face_features, (B, F, 3, D))
+    g_xy = torch.empty_like(face_vertices_image)
+    g_ff = torch.empty_like(face_features)
+    with torch.cuda.device(dev):
+        st = _lib.lib().dibr_b200_deftet_sparse_render_backward(
+            B, F, P, K, D, _ptr(grad_interpolated_features), _ptr(face_idx), _ptr(weights),
+            _ptr(face_vertices_image), _ptr(face_features), float(eps), _ptr(g_xy), _ptr(g_ff), _stream(dev))
+    _lib.check(st, fn)
+    return [g_xy, g_ff]
+
+
 # kaolin._C.render.mesh.<op> namespace, as bindings.cpp:42,111-115 lays it out
 render = types.SimpleNamespace(mesh=types.SimpleNamespace(
     packed_rasterize_forward_cuda=packed_rasterize_forward_cuda,
     rasterize_backward_cuda=rasterize_backward_cuda,
     dibr_soft_mask_forward_cuda=dibr_soft_mask_forward_cuda,
     dibr_soft_mask_backward_cuda=dibr_soft_mask_backward_cuda,
+    deftet_sparse_render_forward_cuda=deftet_sparse_render_forward_cuda,
+    deftet_sparse_render_backward_cuda=deftet_sparse_render_backward_cuda,
 ))

@@ -13,7 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(_HERE, "csrc")
 # DIBR_B200_LIB: an alternative build of the same sources (A/B experiments on the GPU box only)
 LIB_PATH = os.environ.get("DIBR_B200_LIB") or os.path.join(CSRC, "libdibr_b200.so")
-SOURCES = [os.path.join(CSRC, "dibr_b200.cu"), os.path.join(CSRC, "mesh_pipeline.cu")]
+SOURCES = [os.path.join(CSRC, "dibr_b200.cu"), os.path.join(CSRC, "mesh_pipeline.cu"),
+           os.path.join(CSRC, "deftet.cu")]
 HEADERS = [os.path.join(CSRC, "dibr_math.cuh"),
            os.path.join(_HERE, "..", "include", "dibr_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -63,6 +64,12 @@ SIGNATURES = {
     "dibr_b200_texture_mapping_backward": (_i, [_i, _i64, _i, _i, _i, _vp, _vp, _i, _vp, _vp, _vp, _vp]),
     "dibr_b200_mask_iou_forward": (_i, [_i, _i64, _vp, _vp, _vp, _vp, _vp]),
     "dibr_b200_mask_iou_backward": (_i, [_i, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    # DefTet volumetric renderer operators (csrc/deftet.cu)
+    "dibr_b200_deftet_workspace_bytes": (_sz, [_i, _i]),
+    "dibr_b200_deftet_sparse_render_forward": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f,
+                                                    _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dibr_b200_deftet_sparse_render_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f,
+                                                     _vp, _vp, _vp]),
 }
 
 

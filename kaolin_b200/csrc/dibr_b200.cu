@@ -2125,16 +2125,25 @@ struct RwCfg {
   static constexpr int pad_odd(int bytes) { return ((bytes / 16) & 1) ? bytes : bytes + 16; }
   static constexpr int kIdxPitch = pad_odd(kRwSlab * 8);        // 32 -> 48
   static constexpr int kWPitch = pad_odd(kRwSlab * 12);         // 48
-  static constexpr int kGRow = kRwSlab * DT * 4;                // 16*D
-  static constexpr int kGPitch = pad_odd(kGRow);
-  static constexpr int kStage = 32 * (kIdxPitch + kWPitch + kGPitch);
   static constexpr int kVals = 6 + 3 * DT;
   static constexpr int kAcc = (kVals + 3) & ~3;                 // floats per face record
+};
+// upstream-gradient rows: fp32 (16*D bytes, 16-byte chunks) or bf16 (8*D bytes; D odd -> 8-byte chunks,
+// rows of 24 bytes are read with LDS.64: a half warp covers the 32 banks)
+template <int DT, typename FT>
+struct RwG {
+  static constexpr int kRow = kRwSlab * DT * (int)sizeof(FT);
+  static constexpr int kChunk = (kRow % 16) ? 8 : 16;
+  static constexpr int kPitch = kChunk == 16 ? RwCfg<DT>::pad_odd(kRow) : kRow;
+  static constexpr int kStage = 32 * (RwCfg<DT>::kIdxPitch + RwCfg<DT>::kWPitch + kPitch);
 };
 constexpr int kAccMax = 20;  // D = 4
 
 __device__ __forceinline__ void cp_async16(void* dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async8(void* dst, const void* src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(dst)), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
@@ -2142,7 +2151,7 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 
 struct RowBwdArgs {
   int B, H, W, F, strip, jobs_x, jobs_y;
-  const float* grad_feat; const int64_t* idx; const float* w; const float* xy; const float* feat;
+  const void* grad_feat; const int64_t* idx; const float* w; const float* xy; const void* feat;   // FT: float | bf16
   float eps;
   float* acc;    // [B*F][RwCfg<D>::kAcc], zeroed
   int* job_ctr;  // [1] zeroed (lives right behind the records)
@@ -2156,14 +2165,14 @@ struct RowFace {          // constants of the face a lane is currently accumulat
   float d1[DT], d2[DT];
 };
 
-template <int DT>
+template <int DT, typename FT>
 __device__ __forceinline__ void row_face_load(const RowBwdArgs& a, int64_t face, RowFace<DT>& c) {
   const float2* pp = reinterpret_cast<const float2*>(a.xy + face * 6);
   const float2 pa = __ldg(pp), pb = __ldg(pp + 1), pc = __ldg(pp + 2);
-  const float* cf = a.feat + face * 3 * DT;
+  const FT* cf = static_cast<const FT*>(a.feat) + face * 3 * DT;
   float c0[DT], c1[DT], c2[DT];
 #pragma unroll
-  for (int d = 0; d < DT; ++d) { c0[d] = __ldg(cf + d); c1[d] = __ldg(cf + DT + d); c2[d] = __ldg(cf + 2 * DT + d); }
+  for (int d = 0; d < DT; ++d) { c0[d] = Feat<FT>::ld(cf + d); c1[d] = Feat<FT>::ld(cf + DT + d); c2[d] = Feat<FT>::ld(cf + 2 * DT + d); }
   c.ax = pa.x; c.ay = pa.y; c.bx = pb.x; c.by = pb.y; c.cx = pc.x; c.cy = pc.y;
   c.pp = fsub(c.by, c.ay); c.n = fsub(c.cx, c.ax); c.m = fsub(c.bx, c.ax); c.q = fsub(c.cy, c.ay);
   float k3 = ffma(c.m, c.q, -fmul(c.pp, c.n));
@@ -2218,10 +2227,11 @@ __device__ __forceinline__ void row_pixel(const RowFace<DT>& c, float aw, float 
 #ifndef DIBR_ROWS_MINB
 #define DIBR_ROWS_MINB 20
 #endif
-template <int DT>
+template <int DT, typename FT>
 __global__ void __launch_bounds__(32, DIBR_ROWS_MINB) raster_bwd_rows_kernel(const __grid_constant__ RowBwdArgs a) {
   using C = RwCfg<DT>;
-  __shared__ __align__(128) unsigned char smem[2 * C::kStage];
+  using G = RwG<DT, FT>;
+  __shared__ __align__(128) unsigned char smem[2 * G::kStage];
   const int lane = threadIdx.x;
   // persistent single-warp CTAs pull (view, 32-row band, column strip) jobs from a counter: the
   // jobs differ by 10x in cost (background vs dense mesh), so a static grid ends with a
@@ -2243,7 +2253,7 @@ __global__ void __launch_bounds__(32, DIBR_ROWS_MINB) raster_bwd_rows_kernel(con
   const int64_t fbase = (int64_t)b * a.F;
 
   auto issue = [&](int s, int buf) {
-    unsigned char* base = smem + buf * C::kStage;
+    unsigned char* base = smem + buf * G::kStage;
     const int x = col0 + s * kRwSlab;
 #pragma unroll
     for (int j = 0; j < 2; ++j) {           // face_idx: 2 chunks per row
@@ -2259,13 +2269,16 @@ __global__ void __launch_bounds__(32, DIBR_ROWS_MINB) raster_bwd_rows_kernel(con
         cp_async16(base + 32 * C::kIdxPitch + r * C::kWPitch + ch * 16,
                    reinterpret_cast<const char*>(a.w + (pix0 + (int64_t)r * a.W + x) * 3) + ch * 16);
     }
-    constexpr int GC = C::kGRow / 16;       // upstream gradient: D chunks per row
+    constexpr int GC = G::kRow / G::kChunk;   // upstream gradient: chunks per row
+    const FT* gsrc = static_cast<const FT*>(a.grad_feat);
 #pragma unroll
     for (int j = 0; j < GC; ++j) {
       const int k = lane + 32 * j, r = k / GC, ch = k - r * GC;
-      if (row0 + r < a.H)
-        cp_async16(base + 32 * (C::kIdxPitch + C::kWPitch) + r * C::kGPitch + ch * 16,
-                   reinterpret_cast<const char*>(a.grad_feat + (pix0 + (int64_t)r * a.W + x) * DT) + ch * 16);
+      if (row0 + r < a.H) {
+        unsigned char* dst = base + 32 * (C::kIdxPitch + C::kWPitch) + r * G::kPitch + ch * G::kChunk;
+        const char* src = reinterpret_cast<const char*>(gsrc + (pix0 + (int64_t)r * a.W + x) * DT) + ch * G::kChunk;
+        if (G::kChunk == 16) cp_async16(dst, src); else cp_async8(dst, src);
+      }
     }
     cp_async_commit();
   };
@@ -2286,7 +2299,7 @@ __global__ void __launch_bounds__(32, DIBR_ROWS_MINB) raster_bwd_rows_kernel(con
   for (int s = 0; s < nslabs; ++s) {
     if (s + 1 < nslabs) { issue(s + 1, (s + 1) & 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
     __syncwarp();
-    const unsigned char* base = smem + (s & 1) * C::kStage;
+    const unsigned char* base = smem + (s & 1) * G::kStage;
     if (row_ok) {
       do {
         const ulonglong2* ip = reinterpret_cast<const ulonglong2*>(base + lane * C::kIdxPitch);
@@ -2299,17 +2312,30 @@ __global__ void __launch_bounds__(32, DIBR_ROWS_MINB) raster_bwd_rows_kernel(con
         const float4* wp = reinterpret_cast<const float4*>(base + 32 * C::kIdxPitch + lane * C::kWPitch);
         const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2];
         const float wv[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};
-        const float4* gp = reinterpret_cast<const float4*>(base + 32 * (C::kIdxPitch + C::kWPitch) + lane * C::kGPitch);
         float gv[4 * DT];
+        {
+          const unsigned char* grow = base + 32 * (C::kIdxPitch + C::kWPitch) + lane * G::kPitch;
+          if (std::is_same<FT, float>::value) {
+            const float4* gp = reinterpret_cast<const float4*>(grow);
 #pragma unroll
-        for (int k = 0; k < DT; ++k) { const float4 t = gp[k]; gv[4 * k] = t.x; gv[4 * k + 1] = t.y; gv[4 * k + 2] = t.z; gv[4 * k + 3] = t.w; }
+            for (int k = 0; k < DT; ++k) { const float4 t = gp[k]; gv[4 * k] = t.x; gv[4 * k + 1] = t.y; gv[4 * k + 2] = t.z; gv[4 * k + 3] = t.w; }
+          } else {   // bf16: 2 values per 32-bit word, low half first
+            const uint2* gp = reinterpret_cast<const uint2*>(grow);
+#pragma unroll
+            for (int k = 0; k < DT; ++k) {
+              const uint2 t = gp[k];
+              gv[4 * k] = __uint_as_float(t.x << 16); gv[4 * k + 1] = __uint_as_float(t.x & 0xffff0000u);
+              gv[4 * k + 2] = __uint_as_float(t.y << 16); gv[4 * k + 3] = __uint_as_float(t.y & 0xffff0000u);
+            }
+          }
+        }
 #pragma unroll
         for (int p = 0; p < 4; ++p) {
           if (f[p] != cur) {
             if (cur >= 0) flush();
             cur = f[p];
             if (cur >= 0) {
-              row_face_load<DT>(a, fbase + cur, fc);
+              row_face_load<DT, FT>(a, fbase + cur, fc);
 #pragma unroll
               for (int i = 0; i < C::kAcc; ++i) acc[i] = 0.f;
             }
@@ -2627,7 +2653,7 @@ float* acc_region(void* ws, size_t ws_bytes, int B, int64_t NF, int H, int W) {
   return (float*)(p + Lo.cnt + Lo.off + Lo.mode + Lo.ent);
 }
 
-template <int DT>
+template <int DT, typename FT>
 int launch_rows_t(const RowBwdArgs& a0, int64_t NF, float* g_xy, float* g_ff, int accumulate_xy, cudaStream_t st) {
   RowBwdArgs a = a0;
   a.job_ctr = reinterpret_cast<int*>(a.acc + (size_t)NF * RwCfg<DT>::kAcc);   // kAcc <= 16 < kAccMax: room behind the records
@@ -2644,13 +2670,13 @@ int launch_rows_t(const RowBwdArgs& a0, int64_t NF, float* g_xy, float* g_ff, in
     if (slots == 0) {
       int sms = 148, per_sm = 16;
       cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_bwd_rows_kernel<DT>, 32, 0) != cudaSuccess || per_sm < 1)
+      if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, raster_bwd_rows_kernel<DT, FT>, 32, 0) != cudaSuccess || per_sm < 1)
         per_sm = 16;
       slots = sms * per_sm;
       slots_of[dev & 63] = slots;
     }
     const int64_t jobs = (int64_t)a.jobs_x * a.jobs_y * a.B;
-    raster_bwd_rows_kernel<DT><<<(unsigned)(jobs < slots ? jobs : slots), 32, 0, st>>>(a);
+    raster_bwd_rows_kernel<DT, FT><<<(unsigned)(jobs < slots ? jobs : slots), 32, 0, st>>>(a);
   }
   {
     Span sp("raster_bwd_finalize_kernel", st);
@@ -2661,11 +2687,12 @@ int launch_rows_t(const RowBwdArgs& a0, int64_t NF, float* g_xy, float* g_ff, in
 
 // Row-walk rasterize backward: one warp per 32 rows x strip columns; the strip is as long as
 // still leaves a few waves of single-warp CTAs (longer strips = fewer cut face runs).
+template <typename FT>
 int launch_raster_bwd_rows(const RasterBwdArgs& r, float* acc, int accumulate_xy, cudaStream_t st) {
   RowBwdArgs a;
   a.B = r.B; a.H = r.H; a.W = r.W; a.F = r.F;
-  a.grad_feat = static_cast<const float*>(r.grad_feat); a.idx = r.idx; a.w = r.w; a.xy = r.xy;
-  a.feat = static_cast<const float*>(r.feat); a.eps = r.eps; a.acc = acc;
+  a.grad_feat = r.grad_feat; a.idx = r.idx; a.w = r.w; a.xy = r.xy;
+  a.feat = r.feat; a.eps = r.eps; a.acc = acc;
   a.jobs_y = (r.H + 31) / 32;
   int strip = 32;   // measured on the benchmark scene: 128 -> 0.494, 64 -> 0.526, 32 -> 0.542 of HBM peak
   if (const char* fs = getenv("DIBR_B200_ROWS_STRIP")) { const int v = atoi(fs); if (v >= kRwSlab && v % kRwSlab == 0) strip = v; }
@@ -2674,10 +2701,10 @@ int launch_raster_bwd_rows(const RasterBwdArgs& r, float* acc, int accumulate_xy
   a.jobs_x = (r.W + strip - 1) / strip;
   const int64_t NF = (int64_t)r.B * r.F;
   switch (r.D) {
-    case 1: return launch_rows_t<1>(a, NF, r.grad_xy, r.grad_feat_out, accumulate_xy, st);
-    case 2: return launch_rows_t<2>(a, NF, r.grad_xy, r.grad_feat_out, accumulate_xy, st);
-    case 3: return launch_rows_t<3>(a, NF, r.grad_xy, r.grad_feat_out, accumulate_xy, st);
-    case 4: return launch_rows_t<4>(a, NF, r.grad_xy, r.grad_feat_out, accumulate_xy, st);
+    case 1: return launch_rows_t<1, FT>(a, NF, r.grad_xy, r.grad_feat_out, accumulate_xy, st);
+    case 2: return launch_rows_t<2, FT>(a, NF, r.grad_xy, r.grad_feat_out, accumulate_xy, st);
+    case 3: return launch_rows_t<3, FT>(a, NF, r.grad_xy, r.grad_feat_out, accumulate_xy, st);
+    case 4: return launch_rows_t<4, FT>(a, NF, r.grad_xy, r.grad_feat_out, accumulate_xy, st);
     default: return DIBR_B200_EINVAL;
   }
 }
@@ -2814,9 +2841,9 @@ static int backward_impl(int batch, int num_faces, int height, int width, int fe
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
   const bool run_raster = grad_features && feat_dim > 0;
-  // row-walk kernel: fp32 features, D <= 4, rows a multiple of 4 px, a workspace with the face records
+  // row-walk kernel: fp32 or bf16 features, D <= 4, rows a multiple of 4 px, a workspace with the face records
   float* acc = nullptr;
-  if (run_raster && !bf16 && feat_dim <= 4 && (width % kRwSlab) == 0 && NF > 0) {
+  if (run_raster && feat_dim <= 4 && (width % kRwSlab) == 0 && NF > 0) {
     const char* force = getenv("DIBR_B200_RASTER_BWD");   // "warp": A/B against the warp-reduction kernel
     if (!(force && force[0] == 'w')) acc = acc_region(workspace, workspace_bytes_, batch, NF, height, width);
   }
@@ -2837,7 +2864,8 @@ static int backward_impl(int batch, int num_faces, int height, int width, int fe
     a.grad_feat = grad_features; a.idx = face_idx; a.w = output_weights; a.xy = face_vertices_image;
     a.feat = face_features; a.eps = eps; a.grad_xy = grad_face_vertices_image;
     a.grad_feat_out = grad_face_features;
-    if (acc) rc = launch_raster_bwd_rows(a, acc, (flags & DIBR_B200_ACCUMULATE) ? 1 : 0, st);
+    if (acc) rc = bf16 ? launch_raster_bwd_rows<__nv_bfloat16>(a, acc, (flags & DIBR_B200_ACCUMULATE) ? 1 : 0, st)
+                       : launch_raster_bwd_rows<float>(a, acc, (flags & DIBR_B200_ACCUMULATE) ? 1 : 0, st);
     else rc = bf16 ? launch_raster_bwd<__nv_bfloat16>(a, st) : launch_raster_bwd<float>(a, st);
     if (rc) return rc;
   }

@@ -3,5 +3,7 @@ steps either side of it (``prepare_vertices``, ``texture_mapping``: kaolin/rende
 from .rasterization import rasterize
 from .dibr import dibr_soft_mask, dibr_rasterization
 from .utils import prepare_vertices, texture_mapping
+from .deftet import deftet_sparse_render
 
-__all__ = ["rasterize", "dibr_soft_mask", "dibr_rasterization", "prepare_vertices", "texture_mapping"]
+__all__ = ["rasterize", "dibr_soft_mask", "dibr_rasterization", "prepare_vertices", "texture_mapping",
+           "deftet_sparse_render"]

@@ -44,3 +44,21 @@ def test_mask_iou_oracle_vs_reference_golden():
     (P.mask_iou_torch(l, r) * float(G["mi_gscale"])).backward()
     np.testing.assert_allclose(l.grad.numpy(), G["mi_g_lhs"], rtol=1e-5, atol=1e-7)
     np.testing.assert_allclose(r.grad.numpy(), G["mi_g_rhs"], rtol=1e-5, atol=1e-7)
+
+
+def test_deftet_oracle_vs_reference_naive_golden():
+    from oracle import deftet as DT
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "deftet.npz"))
+    for tag in ("soup", "layers"):
+        knum = int(g[f"{tag}_knum"])
+        feat, idx = DT.sparse_render(g[f"{tag}_pix"], g[f"{tag}_rr"], g[f"{tag}_fvz"], g[f"{tag}_fvi"], g[f"{tag}_ff"], knum)
+        assert np.array_equal(idx, g[f"{tag}_idx"]), tag
+        np.testing.assert_allclose(feat, g[f"{tag}_feat"], rtol=1e-4, atol=1e-5)
+        t = lambda k, grad=False: torch.from_numpy(g[f"{tag}_{k}"]).requires_grad_(grad)
+        fvi, ff = t("fvi", True), t("ff", True)
+        f2, i2 = DT.sparse_render_torch(t("pix"), t("rr"), t("fvz"), fvi, ff, knum)
+        assert np.array_equal(i2.numpy(), g[f"{tag}_idx"]), tag
+        (f2 * t("gw")).sum().backward()
+        np.testing.assert_allclose(ff.grad.numpy(), g[f"{tag}_g_ff"], rtol=1e-4, atol=1e-5)
+        scale = np.abs(g[f"{tag}_g_fvi"]).max()
+        assert np.abs(fvi.grad.numpy() - g[f"{tag}_g_fvi"]).max() <= 1e-4 * scale
