@@ -269,7 +269,7 @@ __device__ __forceinline__ void bin_insert(const Scene& s, BinSmem& sm, int set,
 // AGG = false (sparse meshes, a few faces per tile): plain atomics, no table.
 template <bool FILL, bool AGG>
 __global__ void __launch_bounds__(AGG ? kBinThreadsAgg : kBinThreadsPlain, AGG ? 2 : 4)
-bin_faces_kernel(Scene s, int sets) {
+bin_faces_kernel(Scene s, int sets, int warp_agg) {
   constexpr int kBinThreads = AGG ? kBinThreadsAgg : kBinThreadsPlain;
   __shared__ typename std::conditional<AGG, BinSmem, int>::type sm;
   const int tid = threadIdx.x;
@@ -314,6 +314,29 @@ bin_faces_kernel(Scene s, int sets) {
     if constexpr (AGG) {
       aggregated = __all_sync(kFull, small);
       if (aggregated) bin_insert(s, sm, set, b, sp[set], where[set]);
+    }
+    if (!aggregated && !AGG && warp_agg && __all_sync(kFull, small)) {
+      // sparse meshes: neighbours in the index buffer are neighbours on screen, so the lanes of a
+      // warp hit a handful of distinct counters; lanes that share one are found with match.any
+      // and their leader issues ONE global atomic for all of them
+      aggregated = true;
+      const int lane = tid & 31;
+      const int4 e = make_int4(f, r[set].x_lo | (r[set].x_hi << 16), r[set].y_lo | (r[set].y_hi << 16), 0);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        where[set][k] = -1;
+        const int bx = sp[set].bx0 + (k & 1), by = sp[set].by0 + (k >> 1);
+        const bool on = sp[set].has && bx <= sp[set].bx1 && by <= sp[set].by1;
+        const unsigned act = __ballot_sync(kFull, on);
+        if (!on) continue;
+        const size_t ci = ((size_t)set * s.B + b) * s.NB + s.bin_base[sp[set].l] + by * s.ntx[sp[set].l] + bx;
+        const unsigned peers = __match_any_sync(act, (unsigned long long)ci);
+        const int leader = __ffs(peers) - 1;
+        int base = 0;
+        if (lane == leader) base = atomicAdd(s.cnt + ci, __popc(peers));
+        base = __shfl_sync(peers, base, leader);
+        if (FILL) s.entries[(size_t)set * 4 * s.NF + 4 * fbase + s.off[ci] + base + __popc(peers & ((1u << lane) - 1u))] = e;
+      }
     }
     if (!aggregated) {
       // (also: a warp with a face of the coarsest level spanning more than 2x2 bins)
@@ -579,7 +602,7 @@ __device__ __forceinline__ void raster_tile(const Scene& s, const TileCtx& c, co
   for (int k = 0; k < nrounds; ++k) {
     if (tid == 0 && k + 1 < nrounds) issue(k + 1);  // buffer (k+1)&1 was released by the sync ending round k-1
     const int cnt = min(kChunk, total - k * kChunk);
-    mbar_wait(&sm.bar[k & 1], (uint32_t)((k >> 1) & 1));
+    if ((tid & ~31) < cnt) mbar_wait(&sm.bar[k & 1], (uint32_t)((k >> 1) & 1));   // only the warps that read the buffer poll
 
     // cull against the tile, gather the face record (candidate id = position in the round)
     uint32_t m = 0;
@@ -1724,6 +1747,8 @@ __global__ void __launch_bounds__(kThreads, DIBR_ENUM_MINB) soft_enum_kernel(con
         sm.cnt_c[tid] = 0;
         __syncthreads();
         // every uncovered pixel claims ALL its remaining faces of this chunk (index order, <= knum)
+        // (a warp-uniform candidate loop with one ballot + one atomic per (warp, candidate) was
+        // measured slower: 0.47 vs 0.37 ms)
         int took = 0;
         if (active) {
           for (int g = 0; g < ngroups && kid + took < K; ++g) {
@@ -2539,13 +2564,15 @@ int build_bins(const Scene& s, int sets, cudaStream_t st) {
   if (e != cudaSuccess) return (int)e;
   if (s.NF > 0) {
     const bool agg = s.NF / s.B >= (int64_t)32 * s.ntx[0] * s.nty[0];
+    const char* fb = getenv("DIBR_B200_BIN");          // "warp": match.any-aggregated atomics (measured SLOWER on
+    const int warp_agg = (fb && fb[0] == 'w') ? 1 : 0; // the benchmark mesh: 98 + 89 vs 77 + 76 us; kept as an A/B switch)
     const int threads = agg ? kBinThreadsAgg : kBinThreadsPlain;
     const unsigned blocks = (unsigned)((s.NF + threads - 1) / threads);
     // dense meshes (tens of faces per 16x16 tile) hammer a few counters: aggregate per CTA
     {
       Span sp("bin_faces_kernel<count>", st);
-      if (agg) bin_faces_kernel<false, true><<<blocks, threads, 0, st>>>(s, sets);
-      else bin_faces_kernel<false, false><<<blocks, threads, 0, st>>>(s, sets);
+      if (agg) bin_faces_kernel<false, true><<<blocks, threads, 0, st>>>(s, sets, 0);
+      else bin_faces_kernel<false, false><<<blocks, threads, 0, st>>>(s, sets, warp_agg);
     }
     {
       Span sp("scan_bins_kernel", st);
@@ -2553,8 +2580,8 @@ int build_bins(const Scene& s, int sets, cudaStream_t st) {
     }
     {
       Span sp("bin_faces_kernel<fill>", st);
-      if (agg) bin_faces_kernel<true, true><<<blocks, threads, 0, st>>>(s, sets);
-      else bin_faces_kernel<true, false><<<blocks, threads, 0, st>>>(s, sets);
+      if (agg) bin_faces_kernel<true, true><<<blocks, threads, 0, st>>>(s, sets, 0);
+      else bin_faces_kernel<true, false><<<blocks, threads, 0, st>>>(s, sets, warp_agg);
     }
   }
   return (int)cudaGetLastError();
@@ -2563,18 +2590,35 @@ int build_bins(const Scene& s, int sets, cudaStream_t st) {
 dim3 tile_grid(const Scene& s) { return dim3((unsigned)s.ntx[0], (unsigned)s.nty[0], (unsigned)s.B); }
 
 // Persistent kernels: one resident wave (SMs x CTAs that fit per SM), never more than the tiles.
+// The wave size is a property of (device, kernel): queried once and cached in a per-instantiation
+// table (idempotent writes of the same value, safe from any thread) - the occupancy / attribute
+// queries cost ~0.1 ms of host time per step on small problems when repeated on every call.
+struct WaveEntry { const void* kernel; int dev; int wave; };
+constexpr int kWaveSlots = 64;
+WaveEntry g_waves[kWaveSlots];   // append-only; a lost race re-queries and stores the same value again
+
 template <typename Kernel>
 unsigned persistent_grid(const Scene& s, Kernel kernel, size_t dyn_smem = 0) {
-  int dev = 0, sms = 148, per_sm = 2;
-  if (cudaGetDevice(&dev) == cudaSuccess) {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const void* key = reinterpret_cast<const void*>(kernel);   // kernels with one signature share this template
+  int wave = 0;
+  for (int i = 0; i < kWaveSlots && g_waves[i].kernel; ++i)
+    if (g_waves[i].kernel == key && g_waves[i].dev == dev) { wave = g_waves[i].wave; break; }
+  if (wave == 0) {
+    int sms = 148, per_sm = 2;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (dyn_smem > 48 * 1024)
+      cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_smem);
     if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, kThreads, dyn_smem) != cudaSuccess ||
         per_sm < 1)
       per_sm = 2;
+    wave = sms * per_sm;
+    for (int i = 0; i < kWaveSlots; ++i)
+      if (!g_waves[i].kernel) { g_waves[i].dev = dev; g_waves[i].wave = wave; g_waves[i].kernel = key; break; }
   }
   const int64_t ntiles = (int64_t)s.ntx[0] * s.nty[0] * s.B;
-  const int64_t g = (int64_t)sms * per_sm;
-  return (unsigned)(ntiles < g ? ntiles : g);
+  return (unsigned)(ntiles < wave ? ntiles : wave);
 }
 
 template <bool R, bool S, bool K, typename FT = float>
@@ -2588,7 +2632,9 @@ void launch_fwd(const FwdArgs& a0, cudaStream_t st) {
     const char* force = getenv("DIBR_B200_FWD");   // "old" | "s1" | "s2": A/B switches
     const int64_t tiles32 = (int64_t)((a.s.W + 31) / 32) * ((a.s.H + 31) / 32);
     const int64_t faces_per_view = a.s.NF / (a.s.B > 0 ? a.s.B : 1);
-    bool two = R && faces_per_view * 3 / 2 <= 200 * tiles32 && tiles32 * a.s.B >= 2048;
+    // ~ faces per 32x32 tile <= 40: c4 (20 k faces at 1024^2) has 20, c3 (512^2) 80, c2 80, c5 320;
+    // measured: c4 0.86 (S=2) vs 0.90 ms (one tile per CTA), c3 0.75 vs 0.52 ms
+    bool two = R && faces_per_view <= 40 * tiles32 && tiles32 * a.s.B >= 2048;
     if (force && force[0] == 's') two = force[1] == '2';
     const bool v2_single = force && force[0] == 's' && force[1] == '1';
     if ((force && force[0] == 'o') || (!two && !v2_single)) {
@@ -2606,9 +2652,7 @@ void launch_fwd(const FwdArgs& a0, cudaStream_t st) {
     }
   }
   if (S) {
-    cudaFuncSetAttribute(soft_tiles_fwd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)sizeof(SoftSmem));
-    const unsigned g1 = persistent_grid(a.s, soft_tiles_fwd_kernel<K>, sizeof(SoftSmem));
+    const unsigned g1 = persistent_grid(a.s, soft_tiles_fwd_kernel<K>, sizeof(SoftSmem));   // (sets the smem attribute once)
     if (!K && a.cache && a.s.pool_tiles > 0 && a.s.pool_slots != nullptr) {
       // enumerate -> evaluate densely -> fold; tiles beyond the cache take the single-kernel path
       {

@@ -75,10 +75,13 @@ def check_size(func, name, t, shape):
         raise RuntimeError(f"{func}: expected {name} of size {list(shape)}, got {list(t.shape)}")
 
 
-# Screen tiles whose soft-mask hits are cached for backward: every tile if that fits in
-# CACHE_MAX_BYTES (small images: a third of the 16x16 tiles touch the silhouette at 256^2),
-# else as many as fit (1024^2 x 32 views: 28 % of the tiles, the silhouette needs 10 %).
-# Tiles beyond the cache are recomputed in backward: same results, several times slower.
+# Screen tiles that get a soft-mask hit-cache block (forward scratch of the enumerate / evaluate
+# kernels AND the backward's input).  Every tile when that fits in CACHE_MAX_BYTES - at 256^2 a third
+# of the 16x16 tiles touch the silhouette, at 1024^2 a tenth, and the host cannot know the number
+# without a device sync - else as many as fit; tiles beyond the cache take the single-kernel path
+# and are recomputed in backward: same results, several times slower.  Both knobs are module
+# attributes (a caller with many live forward graphs can lower CACHE_MAX_BYTES); callers that need
+# no gradient do not keep the workspace alive (render/mesh/dibr.py).
 CACHE_TILE_FRACTION = 1.0
 CACHE_MIN_TILES = 64
 CACHE_MAX_BYTES = 4 << 30
@@ -91,12 +94,20 @@ def cache_tiles_for(batch, height, width, knum):
     return min(tiles, want, max(1, CACHE_MAX_BYTES // (3072 * knum + 17500)))
 
 
+_ws_bytes = {}     # (batch, faces, H, W, knum, cache policy) -> bytes: a pure function of the shape
+
+
 def workspace(batch, total_faces, height, width, device, knum=0):
-    if knum > 0:
-        want = cache_tiles_for(batch, height, width, knum)
-        n = _lib.lib().dibr_b200_workspace_bytes_cached(batch, total_faces, height, width, knum, want)
-    else:
-        n = _lib.lib().dibr_b200_workspace_bytes(batch, total_faces, height, width)
+    key = (batch, total_faces, height, width, knum, CACHE_TILE_FRACTION, CACHE_MAX_BYTES)
+    n = _ws_bytes.get(key)
+    if n is None:
+        if knum > 0:
+            want = cache_tiles_for(batch, height, width, knum)
+            n = _lib.lib().dibr_b200_workspace_bytes_cached(batch, total_faces, height, width, knum, want)
+        else:
+            n = _lib.lib().dibr_b200_workspace_bytes(batch, total_faces, height, width)
+        if len(_ws_bytes) < 4096:
+            _ws_bytes[key] = n
     if n == 0:
         raise RuntimeError("kaolin_b200: unsupported problem size "
                            f"(batch={batch}, faces={total_faces}, image={height}x{width})")

@@ -31,7 +31,8 @@ class DibrSoftMaskB200(Function):
                                           multiplier, 0., sigmainv, boxlen_m, knum, face_idx_in=idx)
         ctx.save_for_backward(soft, fvi, idx)
         ctx.params = (sigmainv, boxlen_m, knum, multiplier)
-        ctx.ws = ws
+        # the workspace (bins + hit cache, up to CACHE_MAX_BYTES) is only worth keeping for a backward
+        ctx.ws = ws if ctx.needs_input_grad[0] else None      # (grad mode is off inside forward: do not test it)
         return soft
 
     @staticmethod
@@ -40,7 +41,7 @@ class DibrSoftMaskB200(Function):
         sigmainv, boxlen_m, knum, multiplier = ctx.params
         B, H, W = idx.shape
         g_fvi, _ = _host.backward(H, W, None, grad_soft_mask.contiguous(), idx, None, soft, fvi, None,
-                                  multiplier, 0., sigmainv, boxlen_m, knum, ctx.ws, True)
+                                  multiplier, 0., sigmainv, boxlen_m, knum, ctx.ws, ctx.ws is not None)
         return g_fvi, None, None, None, None, None
 
 
@@ -81,7 +82,8 @@ class DibrRasterizationB200(Function):
         ctx.mark_non_differentiable(face_idx)
         ctx.set_materialize_grads(False)   # no 8 B/pixel zero "gradient" for face_idx
         ctx.params = (height, width, multiplier, eps, sigmainv, boxlen_m, knum)
-        ctx.ws = ws
+        # inference / no_grad callers do not pin the workspace (bins + hit cache) until the graph dies
+        ctx.ws = ws if (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]) else None
         return feat, soft, face_idx
 
     @staticmethod
@@ -92,7 +94,7 @@ class DibrRasterizationB200(Function):
         g_soft = None if grad_soft_mask is None else grad_soft_mask.contiguous()
         # per-node hook (set on this node by OverlappedGradAllGather.attach, never global)
         g_fvi, g_ff = _host.backward(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff,
-                                     multiplier, eps, sigmainv, boxlen_m, knum, ctx.ws, True,
+                                     multiplier, eps, sigmainv, boxlen_m, knum, ctx.ws, ctx.ws is not None,
                                      feature_grad_hook=getattr(ctx, "feature_grad_hook", None))
         g_ff = g_ff.to(ff.dtype)      # fp32 accumulation; autograd wants the input's dtype (bf16 features)
         return None, None, None, g_fvi, g_ff, None, None, None, None, None, None, None

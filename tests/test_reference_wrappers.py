@@ -21,6 +21,7 @@ from kaolin_b200 import synthetic
 
 @pytest.mark.skipif(not ref_import.available(), reason="/root/reference not present (GPU box)")
 def test_reference_wrappers_reach_the_shim_with_the_right_arity():
+    import inspect
     ref_import.setup(b200_C)
     rast = ref_import.module("kaolin.render.mesh.rasterization")
     dibr = ref_import.module("kaolin.render.mesh.dibr")
@@ -34,8 +35,13 @@ def test_reference_wrappers_reach_the_shim_with_the_right_arity():
         dibr.dibr_soft_mask(t(fvi), torch.full((1, 32, 32), -1, dtype=torch.long))
     with pytest.raises(RuntimeError, match="GPU|CUDA|no CPU path"):
         dibr.dibr_rasterization(32, 32, t(fvz), t(fvi), t(ff), t(fnz))
+    dt = ref_import.module("kaolin.render.mesh.deftet")
+    assert dt._C is b200_C
+    with pytest.raises(RuntimeError, match="GPU|CUDA|no CPU path"):        # deftet.py:292-299 -> the shim
+        dt.deftet_sparse_render(torch.zeros(1, 5, 2), torch.zeros(1, 5, 2), t(fvz), t(fvi), t(ff), knum=4)
+    assert len(inspect.signature(b200_C.render.mesh.deftet_sparse_render_forward_cuda).parameters) == 7
+    assert len(inspect.signature(b200_C.render.mesh.deftet_sparse_render_backward_cuda).parameters) == 6
     # backward operators: arity of the shim == arity of the reference's call sites
-    import inspect
     sig = lambda f: len(inspect.signature(f).parameters)
     assert sig(b200_C.render.mesh.packed_rasterize_forward_cuda) == 9      # rasterization.py:329-339
     assert sig(b200_C.render.mesh.rasterize_backward_cuda) == 7            # rasterization.py:360-368
