@@ -56,6 +56,8 @@ def parse():
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--no-ref-cuda", action="store_true")
     p.add_argument("--no-e2e-images", action="store_true")
+    p.add_argument("--e2e-graph", action="store_true",
+                   help="N = 1: also time the public API's CUDA-graph fast path (make_graphed_dibr_rasterization)")
     p.add_argument("--ref-cuda-views", type=int, default=2)
     p.add_argument("--features", default="fp32", choices=["fp32", "bf16"],
                    help="storage of face_features / features / grad_features (arithmetic is fp32 either "
@@ -555,6 +557,33 @@ def run_ours(args):
                       "d2h_bytes_per_step": d2h + sum(x.numel() * x.element_size() for x in h_img)}
         del h_img
 
+    # ---- e2e through the CUDA-graph fast path of the public API (launch-bound sizes) --------
+    e2e_graphed = None
+    if world == 1 and args.e2e_graph:
+        from kaolin_b200.render.mesh import make_graphed_dibr_rasterization
+        a_fvz, a_fvi, a_ff, a_fnz = dev_in[0]
+        fgraph = make_graphed_dibr_rasterization(H, W, a_fvz, a_fvi, a_ff, a_fnz, SIGMAINV, BOXLEN, KNUM)
+
+        def step_graphed():
+            with torch.no_grad():
+                a_fvz.copy_(h_fvz, non_blocking=True); a_fvi.copy_(h_fvi, non_blocking=True)
+                a_ff.copy_(h_ff, non_blocking=True); a_fnz.copy_(h_fnz, non_blocking=True)
+            a_fvi.grad = None; a_ff.grad = None
+            feat, soft, idx = fgraph(a_fvz, a_fvi, a_ff, a_fnz)
+            torch.autograd.backward([feat, soft], [g_feat, g_soft])
+            host_out[0][0].copy_(a_fvi.grad, non_blocking=True); host_out[0][1].copy_(a_ff.grad, non_blocking=True)
+        for _ in range(3):
+            step_graphed()
+        torch.cuda.synchronize()
+        start.record()
+        for _ in range(args.steps):
+            step_graphed()
+        end.record(); torch.cuda.synchronize()
+        gms = start.elapsed_time(end) / args.steps
+        e2e_graphed = {"value": B * H * W / (gms * 1e-3) / 1e6, "unit": UNIT, "ms_per_step": gms,
+                       "api": "kaolin_b200.render.mesh.make_graphed_dibr_rasterization (forward and backward replayed "
+                              "from CUDA graphs), same H2D / D2H as e2e, single-buffered"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -645,7 +674,7 @@ def run_ours(args):
                                 "device for the loss that consumes them - see e2e_images for the variant that "
                                 "downloads them too",
                 "host_wall_ms_per_step": wall_ms / args.steps},
-        "e2e_images": e2e_images,
+        "e2e_images": e2e_images, "e2e_graphed": e2e_graphed,
         "gpu_launches": max(1, len(kernel_order)) * len(spans) * args.steps,   # kernels per (chunk of a) step, as traced
         "roofline": roofline,
         "triangle_pixel_tests_per_s": {

@@ -1923,7 +1923,7 @@ __global__ void __launch_bounds__(kThreads) soft_bwd_dense_kernel(const __grid_c
 // them with three RED.v2 when the face changes - no match/shuffle reduction (30 SHFL per warp at
 // 1 SHFL per clock per SM in the kernel above) and one face-vertex load per run instead of per hit.
 #ifndef DIBR_SBWD_MINB
-#define DIBR_SBWD_MINB 3
+#define DIBR_SBWD_MINB 4   /* 64 registers (12 B of spills), 32 warps/SM: 0.290 vs 0.303 ms at 3 */
 #endif
 __global__ void __launch_bounds__(kThreads, DIBR_SBWD_MINB) soft_bwd_runs_kernel(const __grid_constant__ SoftBwdArgs a) {
   const Scene& s = a.s;
@@ -2334,6 +2334,16 @@ __global__ void __launch_bounds__(32, DIBR_ROWS_MINB) raster_bwd_rows_kernel(con
 #pragma unroll
         for (int p = 0; p < 4; ++p) { f[p] = f[p] < 0 ? -1 : f[p]; any = any || f[p] >= 0; }
         if (!any) break;
+        // the faces this block will switch to: pull their records towards L1 now (the demand loads in
+        // row_face_load were 45 % of this kernel's stall samples)
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          const int prev = p ? f[p - 1] : cur;
+          if (f[p] >= 0 && f[p] != prev) {
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.xy + (fbase + f[p]) * 6));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(static_cast<const FT*>(a.feat) + (fbase + f[p]) * 3 * DT));
+          }
+        }
         const float4* wp = reinterpret_cast<const float4*>(base + 32 * C::kIdxPitch + lane * C::kWPitch);
         const float4 w0 = wp[0], w1 = wp[1], w2 = wp[2];
         const float wv[12] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w, w2.x, w2.y, w2.z, w2.w};

@@ -36,8 +36,9 @@ def main():
     ci = {h: i for i, h in enumerate(hdr)}
     tmp = tempfile.mkdtemp()
     subprocess.run(["cuobjdump", "-xelf", "all", os.path.abspath(lib)], cwd=tmp, capture_output=True)
-    cubin = [f for f in os.listdir(tmp) if f.endswith(".cubin")][0]
-    dis = subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
+    dis = ""      # the library holds one cubin per translation unit
+    for cubin in sorted(f for f in os.listdir(tmp) if f.endswith(".cubin")):
+        dis += "\n" + subprocess.run(["nvdisasm", "-gi", "-c", os.path.join(tmp, cubin)], capture_output=True, text=True).stdout
     # find the function whose demangled name matches: use the template signature in kname
     funcs = re.split(r"\n//-+ \.text\.", dis)
     pick = None
