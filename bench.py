@@ -354,11 +354,13 @@ def run_ours(args):
         step_resident()
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(3 * len(spans))] for _ in range(args.steps)]
     start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    # clocks are sampled on rank 0 only: 8 nvidia-smi pollers at 20 ms inside a 100 ms window
-    # were one suspect for round 1's slow N = 8 resident number
+    # clocks are sampled on rank 0 only (8 nvidia-smi pollers at 20 ms inside a 100 ms window were one
+    # suspect for round 1's slow N = 8 number) and the poller is spawned BEFORE the barrier: spawning it
+    # after made rank 0 enter the timed loop milliseconds late, and every other rank's first all-gather
+    # waited for it (one 3.5 ms step per rank in the first N = 8 run of this round)
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ else local) \
         if rank == 0 else None
+    barrier()
     start.record()
     for k in range(args.steps):
         step_resident(evs[k])

@@ -77,7 +77,8 @@ def main():
                      "gathered_shape": list(g_fvi.shape)}
         ok = ok and same and e1 <= 1e-5 and e2 <= 1e-5 and tuple(g_fvi.shape) == tuple(full["g_fvi"].shape)
     out["ok"] = bool(ok)
-    print("MGPU_RESULT " + json.dumps(out), flush=True)
+    sys.stdout.write("\nMGPU_RESULT " + json.dumps(out) + "\n")     # one write per rank
+    sys.stdout.flush()
     dist.barrier()
     dist.destroy_process_group()
     sys.exit(0 if ok else 1)

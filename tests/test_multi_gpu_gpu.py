@@ -21,8 +21,16 @@ def test_sharded_nccl_equals_single_gpu():
            "--master-addr", "127.0.0.1", "--master-port", str(port),
            os.path.join(ROOT, "tests", "_mgpu_worker.py")]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=900, cwd=ROOT)
-    results = [json.loads(line.split("MGPU_RESULT ", 1)[1]) for line in r.stdout.splitlines()
-               if "MGPU_RESULT " in line]
+    # the two ranks write to the same pipe: their lines can interleave, so parse every object that
+    # follows a marker instead of whole lines
+    dec, results, pos = json.JSONDecoder(), [], 0
+    while True:
+        pos = r.stdout.find("MGPU_RESULT ", pos)
+        if pos < 0:
+            break
+        obj, end = dec.raw_decode(r.stdout, pos + len("MGPU_RESULT "))
+        results.append(obj)
+        pos = end
     print(r.stdout[-3000:], r.stderr[-3000:])
     assert r.returncode == 0, r.stderr[-2000:]
     assert len(results) == world and all(x["ok"] for x in results)
