@@ -68,6 +68,11 @@ def parse():
     p.add_argument("--graph", action="store_true",
                    help="N = 1: capture the resident forward+backward step in a CUDA graph and time replays "
                         "(what launch-bound sizes such as c2 gain from it)")
+    p.add_argument("--bwd-chunks", type=int, default=None,
+                   help="N > 1: view chunks of the BACKWARD (dibr_b200_backward_views); chunk i's gradient all-gathers "
+                        "travel while chunk i+1 computes. Default 1 (the feature gradient's gather overlaps the "
+                        "soft-mask branch): measured at N = 2, two chunks cost +0.15 ms of backward compute "
+                        "(half-size launches) for at most 0.1 ms of hidden exchange at N = 8")
     p.add_argument("--chunks", type=int, default=1,
                    help="N > 1: 1 = the all-gather of grad_face_features overlaps the soft-mask branch of "
                         "the backward (default); k > 1 = k view-chunks per step, chunk i's all-gather "
@@ -260,7 +265,8 @@ def run_ours(args):
     import torch.distributed as dist
     from kaolin_b200 import _lib
     from kaolin_b200.render.mesh import _host, dibr_rasterization
-    from kaolin_b200.multi_gpu import ChunkedGradAllGather, OverlappedGradAllGather, chunk_ranges
+    from kaolin_b200.multi_gpu import (ChunkedGradAllGather, OverlappedGradAllGather, PipelinedGradAllGather,
+                                       chunk_ranges, pipelined_backward_all_gather)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -307,6 +313,8 @@ def run_ours(args):
     # N > 1: the all-gather of grad_face_features (final after the rasterize branch of the
     # backward) travels while the soft-mask branch runs; grad_face_vertices_image follows.
     spans = chunk_ranges(B, args.chunks) if world > 1 else [(0, B)]
+    bwd_chunks = args.bwd_chunks if args.bwd_chunks is not None else 1
+    pipelined = world > 1 and len(spans) == 1 and bwd_chunks > 1
 
     def step_resident(ev=None):
         chunked = ChunkedGradAllGather(B) if world > 1 and len(spans) > 1 else None
@@ -318,7 +326,15 @@ def run_ours(args):
             bwd = lambda hook=None: _host.backward(H, W, g_feat[c0:c1], g_soft[c0:c1], idx, wts, soft,
                                                    d_fvi[c0:c1], d_ff[c0:c1], MULT, EPS, SIGMAINV, boxlen_m,
                                                    KNUM, ws, True, feature_grad_hook=hook)
-            if world > 1 and chunked is None:
+            if pipelined:
+                l_fvi = torch.empty_like(d_fvi)
+                l_ff = torch.empty(d_ff.shape, dtype=torch.float32, device=dev)
+                run = lambda v0, v1, hook: _host.backward(H, W, g_feat, g_soft, idx, wts, soft, d_fvi, d_ff, MULT, EPS,
+                                                          SIGMAINV, boxlen_m, KNUM, ws, True, feature_grad_hook=hook,
+                                                          views=(v0, v1), out=(l_fvi, l_ff))
+                g_fvi, g_ff = pipelined_backward_all_gather(B, bwd_chunks, run, l_fvi, l_ff)
+                if ev: ev[3 * ci + 2].record()
+            elif world > 1 and chunked is None:
                 gather = OverlappedGradAllGather(B * world)
                 g_fvi, g_ff = bwd(gather.hook)
                 if ev: ev[3 * ci + 2].record()
@@ -463,9 +479,14 @@ def run_ours(args):
         elif len(spans) == 1:
             a_fvi.grad = None; a_ff.grad = None
             feat, soft, idx = dibr_rasterization(H, W, a_fvz, a_fvi, a_ff, a_fnz, SIGMAINV, BOXLEN, KNUM)
-            gather = OverlappedGradAllGather(B * world).attach(soft)
-            torch.autograd.backward([feat, soft], [g_feat, g_soft])
-            full = gather.finish(a_fvi.grad, a_ff.grad)
+            if pipelined:
+                gather = PipelinedGradAllGather(chunks=bwd_chunks).attach(soft)
+                torch.autograd.backward([feat, soft], [g_feat, g_soft])
+                full = gather.finish()
+            else:
+                gather = OverlappedGradAllGather(B * world).attach(soft)
+                torch.autograd.backward([feat, soft], [g_feat, g_soft])
+                full = gather.finish(a_fvi.grad, a_ff.grad)
             g1, g2 = full[0][rank * B:(rank + 1) * B], full[1][rank * B:(rank + 1) * B]
             loss = (soft.detach().sum() / soft.numel()).reshape(1)
         else:
@@ -661,7 +682,9 @@ def run_ours(args):
                    "width": W, "feat_dim": D, "features": args.features, "cuda_graph": bool(args.graph and world == 1), "knum": KNUM, "sigmainv": SIGMAINV,
                    "boxlen": BOXLEN, "covered_fraction": covered,
                    "parallelism": (f"views sharded x{world}; NCCL all-gather of per-view grads, "
-                                   + ("grad_face_features' gather overlapped with the soft-mask backward"
+                                   + (f"backward in {bwd_chunks} view chunks, chunk i's gathers overlap chunk i+1"
+                                      if pipelined else
+                                      "grad_face_features' gather overlapped with the soft-mask backward"
                                       if len(spans) == 1 else
                                       f"{len(spans)} view-chunks per step, chunk i's gather overlaps chunk i+1"))
                    if world > 1 else "single GPU",

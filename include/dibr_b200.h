@@ -123,6 +123,24 @@ int dibr_b200_backward(
     void* workspace, size_t workspace_bytes, int flags, dibr_b200_stream_t stream);
 
 /*
+ * dibr_b200_backward restricted to the views [view_begin, view_end) of the batch.  ALL pointers are
+ * the full-batch tensors and the forward's workspace (exactly what dibr_b200_backward takes;
+ * grad_features / face_features hold bfloat16 bit patterns when features_bf16 != 0); only the rows
+ * of grad_face_vertices_image / grad_face_features that belong to those views are written.  Lets a
+ * caller pipeline the backward of one view chunk with the exchange (all-gather) of the previous
+ * chunk's gradients: kaolin_b200.multi_gpu.pipelined_backward_all_gather.
+ */
+int dibr_b200_backward_views(
+    int batch, int num_faces, int height, int width, int feat_dim,
+    const void* grad_features, const float* grad_soft_mask,
+    const int64_t* face_idx, const float* output_weights, const float* soft_mask,
+    const float* face_vertices_image, const void* face_features, int features_bf16,
+    float multiplier, float eps, float sigmainv, float boxlen_m, int knum,
+    float* grad_face_vertices_image, float* grad_face_features,
+    void* workspace, size_t workspace_bytes, int flags, int view_begin, int view_end,
+    dibr_b200_stream_t stream);
+
+/*
  * bf16 feature storage (BASELINE.json configs[3], "bf16 features"; an extension - the
  * reference dispatches float/double only, rasterization_cuda.cu:218): same as
  * dibr_b200_forward / dibr_b200_backward except that face_features (B,F,3,D),

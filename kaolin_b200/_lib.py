@@ -44,6 +44,8 @@ SIGNATURES = {
                                _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dibr_b200_backward": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
                                 _f, _f, _f, _f, _i, _vp, _vp, _vp, _sz, _i, _vp]),
+    "dibr_b200_backward_views": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i,
+                                      _f, _f, _f, _f, _i, _vp, _vp, _vp, _sz, _i, _i, _i, _vp]),
     "dibr_b200_forward_bf16": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _f, _f, _i,
                                     _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dibr_b200_backward_bf16": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -1848,6 +1848,7 @@ struct SoftBwdArgs {
   Scene s;
   float sigmainv; int K;
   int from_list;             // 1: tiles of fb_list only; 0: every tile
+  int view_begin, view_end;  // only tiles / cache blocks of these views (dibr_b200_backward_views)
   const float* grad_soft; const float* soft; const int64_t* idx;
   float* grad_xy;
 };
@@ -1859,6 +1860,7 @@ __global__ void __launch_bounds__(kThreads) dibr_tile_soft_bwd_kernel(const __gr
   const int total = a.from_list ? min(*s.fb_ctr, ntiles) : ntiles;
   for (int w = blockIdx.x; w < total; w += gridDim.x) {
     const TileCtx c = tile_ctx_from_linear(s, a.from_list ? s.fb_list[w] : w);
+    if (c.b < a.view_begin || c.b >= a.view_end) continue;   // uniform for the CTA
     __syncthreads();  // previous tile's shared state fully consumed
     load_bin_table(s, c, sm);
     __syncthreads();
@@ -1877,6 +1879,7 @@ __global__ void __launch_bounds__(kThreads) soft_bwd_dense_kernel(const __grid_c
   const int used = min(*s.pool_ctr, s.pool_tiles);
   if ((int)blockIdx.x >= used) return;
   const int4 h = s.pool_hdr[blockIdx.x];  // b, tx, ty, hits
+  if (h.x < a.view_begin || h.x >= a.view_end) return;
   const size_t E = (size_t)256 * s.pool_K;
   const uint32_t* blk = s.pool_data + (size_t)blockIdx.x * 3 * E;
   const int64_t fbase = view_fbase(s, h.x);
@@ -1930,6 +1933,7 @@ __global__ void __launch_bounds__(kThreads, DIBR_SBWD_MINB) soft_bwd_runs_kernel
   const int used = min(*s.pool_ctr, s.pool_tiles);
   if ((int)blockIdx.x >= used) return;
   const int4 h = s.pool_hdr[blockIdx.x];  // b, tx, ty, hits
+  if (h.x < a.view_begin || h.x >= a.view_end) return;
   const size_t E = (size_t)256 * s.pool_K;
   const uint32_t* blk = s.pool_data + (size_t)blockIdx.x * 3 * E;
   const int64_t fbase = view_fbase(s, h.x);
@@ -2876,16 +2880,24 @@ static int backward_impl(int batch, int num_faces, int height, int width, int fe
                          const float* face_vertices_image, const void* face_features,
                          float multiplier, float eps, float sigmainv, float boxlen_m, int knum,
                          float* grad_face_vertices_image, float* grad_face_features, void* workspace,
-                         size_t workspace_bytes_, int flags, dibr_b200_stream_t stream, bool bf16) {
+                         size_t workspace_bytes_, int flags, dibr_b200_stream_t stream, bool bf16,
+                         int view_begin, int view_end) {
   const int64_t NF = (int64_t)batch * num_faces;
   const bool bins_valid = (flags & DIBR_B200_BINS_VALID) != 0;
   int rc = check_dims(batch, NF, height, width);
   if (rc) return rc;
   if (!face_idx || !grad_face_vertices_image || num_faces < 0 || feat_dim < 0) return DIBR_B200_EINVAL;
   if (num_faces > 0 && !face_vertices_image) return DIBR_B200_EINVAL;
+  if (view_begin < 0 || view_end > batch || view_begin >= view_end) return DIBR_B200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   cudaError_t e = cudaSuccess;
   const bool run_raster = grad_features && feat_dim > 0;
+  // the views of this call: rows [view_begin, view_end) of every per-view tensor
+  const int nv = view_end - view_begin;
+  const int64_t NFv = (int64_t)nv * num_faces;
+  const size_t fsz = bf16 ? 2 : 4;
+  float* const g_xy_v = grad_face_vertices_image + (size_t)view_begin * num_faces * 6;
+  float* const g_ff_v = grad_face_features ? grad_face_features + (size_t)view_begin * num_faces * 3 * feat_dim : nullptr;
   // row-walk kernel: fp32 or bf16 features, D <= 4, rows a multiple of 4 px, a workspace with the face records
   float* acc = nullptr;
   if (run_raster && feat_dim <= 4 && (width % kRwSlab) == 0 && NF > 0) {
@@ -2893,22 +2905,26 @@ static int backward_impl(int batch, int num_faces, int height, int width, int fe
     if (!(force && force[0] == 'w')) acc = acc_region(workspace, workspace_bytes_, batch, NF, height, width);
   }
   if (!(flags & DIBR_B200_ACCUMULATE) && !acc) {
-    e = cudaMemsetAsync(grad_face_vertices_image, 0, (size_t)NF * 6 * sizeof(float), st);
+    e = cudaMemsetAsync(g_xy_v, 0, (size_t)NFv * 6 * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
   }
   if (grad_face_features && feat_dim > 0 && (grad_features || !(flags & DIBR_B200_ACCUMULATE)) && !acc) {
-    e = cudaMemsetAsync(grad_face_features, 0, (size_t)NF * 3 * feat_dim * sizeof(float), st);
+    e = cudaMemsetAsync(g_ff_v, 0, (size_t)NFv * 3 * feat_dim * sizeof(float), st);
     if (e != cudaSuccess) return (int)e;
   }
   if (NF == 0) return 0;
   if (run_raster) {
     if (!output_weights || !face_features || !grad_face_features) return DIBR_B200_EINVAL;
     RasterBwdArgs a;
-    a.B = batch; a.H = height; a.W = width; a.F = num_faces; a.D = feat_dim;
+    const size_t px0 = (size_t)view_begin * height * width;
+    a.B = nv; a.H = height; a.W = width; a.F = num_faces; a.D = feat_dim;
     a.ntx = (width + kTile - 1) / kTile; a.nty = (height + kTile - 1) / kTile;
-    a.grad_feat = grad_features; a.idx = face_idx; a.w = output_weights; a.xy = face_vertices_image;
-    a.feat = face_features; a.eps = eps; a.grad_xy = grad_face_vertices_image;
-    a.grad_feat_out = grad_face_features;
+    a.grad_feat = static_cast<const char*>(grad_features) + px0 * feat_dim * fsz;
+    a.idx = face_idx + px0; a.w = output_weights + px0 * 3;
+    a.xy = face_vertices_image + (size_t)view_begin * num_faces * 6;
+    a.feat = static_cast<const char*>(face_features) + (size_t)view_begin * num_faces * 3 * feat_dim * fsz;
+    a.eps = eps; a.grad_xy = g_xy_v;
+    a.grad_feat_out = g_ff_v;
     if (acc) rc = bf16 ? launch_raster_bwd_rows<__nv_bfloat16>(a, acc, (flags & DIBR_B200_ACCUMULATE) ? 1 : 0, st)
                        : launch_raster_bwd_rows<float>(a, acc, (flags & DIBR_B200_ACCUMULATE) ? 1 : 0, st);
     else rc = bf16 ? launch_raster_bwd<__nv_bfloat16>(a, st) : launch_raster_bwd<float>(a, st);
@@ -2925,6 +2941,7 @@ static int backward_impl(int batch, int num_faces, int height, int width, int fe
     s.fnz = nullptr; s.valid = nullptr; s.bbox_tight = nullptr; s.bbox_large = nullptr;
     a.sigmainv = sigmainv; a.K = knum; a.grad_soft = grad_soft_mask; a.soft = soft_mask;
     a.idx = face_idx; a.grad_xy = grad_face_vertices_image;
+    a.view_begin = view_begin; a.view_end = view_end;
     const unsigned persistent = persistent_grid(s, dibr_tile_soft_bwd_kernel);
     if (!bins_valid) {
       // no forward state: rebuild the large bins and recompute every tile
@@ -2964,7 +2981,21 @@ int dibr_b200_backward(int batch, int num_faces, int height, int width, int feat
   return backward_impl(batch, num_faces, height, width, feat_dim, grad_features, grad_soft_mask, face_idx,
                        output_weights, soft_mask, face_vertices_image, face_features, multiplier, eps,
                        sigmainv, boxlen_m, knum, grad_face_vertices_image, grad_face_features, workspace,
-                       workspace_bytes_, flags, stream, false);
+                       workspace_bytes_, flags, stream, false, 0, batch);
+}
+
+int dibr_b200_backward_views(int batch, int num_faces, int height, int width, int feat_dim,
+                             const void* grad_features, const float* grad_soft_mask,
+                             const int64_t* face_idx, const float* output_weights, const float* soft_mask,
+                             const float* face_vertices_image, const void* face_features, int features_bf16,
+                             float multiplier, float eps, float sigmainv, float boxlen_m, int knum,
+                             float* grad_face_vertices_image, float* grad_face_features, void* workspace,
+                             size_t workspace_bytes_, int flags, int view_begin, int view_end,
+                             dibr_b200_stream_t stream) {
+  return backward_impl(batch, num_faces, height, width, feat_dim, grad_features, grad_soft_mask, face_idx,
+                       output_weights, soft_mask, face_vertices_image, face_features, multiplier, eps,
+                       sigmainv, boxlen_m, knum, grad_face_vertices_image, grad_face_features, workspace,
+                       workspace_bytes_, flags, stream, features_bf16 != 0, view_begin, view_end);
 }
 
 int dibr_b200_backward_bf16(int batch, int num_faces, int height, int width, int feat_dim,
@@ -2977,7 +3008,7 @@ int dibr_b200_backward_bf16(int batch, int num_faces, int height, int width, int
   return backward_impl(batch, num_faces, height, width, feat_dim, grad_features, grad_soft_mask, face_idx,
                        output_weights, soft_mask, face_vertices_image, face_features, multiplier, eps,
                        sigmainv, boxlen_m, knum, grad_face_vertices_image, grad_face_features, workspace,
-                       workspace_bytes_, flags, stream, true);
+                       workspace_bytes_, flags, stream, true, 0, batch);
 }
 
 int dibr_b200_packed_rasterize_forward(int batch, int64_t total_faces, int height, int width,

@@ -16,7 +16,8 @@ import torch
 import torch.distributed as dist
 
 __all__ = ["shard_range", "shard_views", "all_gather_view_grads", "chunk_ranges",
-           "ChunkedGradAllGather", "OverlappedGradAllGather"]
+           "ChunkedGradAllGather", "OverlappedGradAllGather", "pipelined_backward_all_gather",
+           "PipelinedGradAllGather"]
 
 
 def shard_range(batch, rank, world_size):
@@ -188,3 +189,72 @@ class OverlappedGradAllGather:
             raise RuntimeError("no feature gradient was produced by the attached backward and none was passed")
         self.work = self.full_ff = self.local_ff = None
         return full_fvi, full_ff
+
+
+def pipelined_backward_all_gather(local_views, chunks, run_chunk, g_fvi, g_ff, group=None):
+    """Backward in view chunks with the gradient exchange of chunk i hidden behind chunk i+1.
+
+    ``run_chunk(c0, c1, hook)`` must issue the backward of the local views [c0, c1) writing rows
+    c0..c1-1 of the full local buffers ``g_fvi`` / ``g_ff`` (``_host.backward(..., views=(c0, c1),
+    out=(g_fvi, g_ff), feature_grad_hook=hook)`` = ``dibr_b200_backward_views``) and call ``hook``
+    once ``g_ff[c0:c1]`` is final (after the rasterize branch).  The all-gathers (asynchronous, on the
+    process group's stream) of a chunk's ``grad_face_features`` start at its hook, those of its
+    ``grad_face_vertices_image`` when the chunk is done; only the last chunk's
+    ``grad_face_vertices_image`` is exposed.  Returns (full_g_fvi, full_g_ff), rank-major like
+    ``all_gather_view_grads``; the current stream waits for the exchange before they are used.
+    """
+    world = dist.get_world_size(group)
+    full_fvi = torch.empty((world, local_views) + tuple(g_fvi.shape[1:]), dtype=g_fvi.dtype, device=g_fvi.device)
+    full_ff = torch.empty((world, local_views) + tuple(g_ff.shape[1:]), dtype=g_ff.dtype, device=g_ff.device)
+    works = []
+    for c0, c1 in chunk_ranges(local_views, chunks):
+        def hook(_g_ff=None, c0=c0, c1=c1):
+            works.append(dist.all_gather([full_ff[r, c0:c1] for r in range(world)], g_ff[c0:c1].contiguous(),
+                                         group=group, async_op=True))
+        run_chunk(c0, c1, hook)
+        works.append(dist.all_gather([full_fvi[r, c0:c1] for r in range(world)], g_fvi[c0:c1].contiguous(),
+                                     group=group, async_op=True))
+    for w in works:
+        w.wait()
+    return (full_fvi.reshape((world * local_views,) + tuple(g_fvi.shape[1:])),
+            full_ff.reshape((world * local_views,) + tuple(g_ff.shape[1:])))
+
+
+class PipelinedGradAllGather:
+    """``pipelined_backward_all_gather`` for the public API: attached to ONE ``dibr_rasterization`` call,
+    it makes that call's autograd backward run in ``chunks`` view chunks (``dibr_b200_backward_views``)
+    whose gradients are exchanged while the next chunk computes.
+
+        feat, soft_mask, face_idx = dibr_rasterization(...)
+        gather = PipelinedGradAllGather(chunks=2).attach(soft_mask)
+        torch.autograd.backward([feat, soft_mask], [g_feat, g_mask])
+        full_g_fvi, full_g_ff = gather.finish()       # rank-major, (world * local_views, F, 3, .)
+
+    Equal shards only.  The local ``.grad`` tensors are produced as usual."""
+
+    def __init__(self, chunks=2, group=None):
+        self.chunks = int(chunks)
+        self.group = group
+        self.result = None
+
+    def _run(self, local_views, run_chunk, g_fvi, g_ff):
+        self.result = pipelined_backward_all_gather(local_views, self.chunks, run_chunk, g_fvi, g_ff, self.group)
+
+    def attach(self, output):
+        node = getattr(output, "grad_fn", None)
+        seen = 0
+        while node is not None and not type(node).__name__.startswith("DibrRasterizationB200") and seen < 4:
+            nxt = [fn for fn, _ in node.next_functions if fn is not None]
+            node = nxt[0] if len(nxt) == 1 else None
+            seen += 1
+        if node is None or not type(node).__name__.startswith("DibrRasterizationB200"):
+            raise ValueError("attach() needs an output of kaolin_b200.render.mesh.dibr_rasterization "
+                             "that requires grad")
+        node.view_pipeline = self._run
+        return self
+
+    def finish(self):
+        if self.result is None:
+            raise RuntimeError("the attached backward has not run (both output gradients are needed)")
+        out, self.result = self.result, None
+        return out

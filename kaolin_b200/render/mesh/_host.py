@@ -141,10 +141,19 @@ def forward(mode, height, width, fvz, fvi, ff, fnz, valid_u8, multiplier, eps,
 
 
 def _backward_call(B, F, height, width, D, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps,
-                   sigmainv, boxlen_m, knum, g_fvi, g_ff, ws, ws_bytes, flags, dev):
+                   sigmainv, boxlen_m, knum, g_fvi, g_ff, ws, ws_bytes, flags, dev, views=None):
     bf16 = ff is not None and ff.dtype == torch.bfloat16
     if g_feat is not None and ff is not None and g_feat.dtype != ff.dtype:
         raise RuntimeError(f"dibr_b200_backward: grad_features is {g_feat.dtype}, face_features is {ff.dtype}")
+    if views is not None:
+        with torch.cuda.device(dev):
+            st = _lib.lib().dibr_b200_backward_views(
+                B, F, height, width, D, ptr(g_feat), ptr(g_soft), ptr(face_idx), ptr(wts), ptr(soft),
+                ptr(fvi), ptr(ff), int(bf16), float(multiplier), float(eps), float(sigmainv), float(boxlen_m),
+                int(knum), ptr(g_fvi), ptr(g_ff), ptr(ws), ws_bytes, int(flags), int(views[0]), int(views[1]),
+                stream_ptr(dev))
+        _lib.check(st, "dibr_b200_backward_views")
+        return
     with torch.cuda.device(dev):
         fn = _lib.lib().dibr_b200_backward_bf16 if bf16 else _lib.lib().dibr_b200_backward
         st = fn(
@@ -155,8 +164,13 @@ def _backward_call(B, F, height, width, D, g_feat, g_soft, face_idx, wts, soft, 
 
 
 def backward(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps,
-             sigmainv, boxlen_m, knum, ws, bins_valid, feature_grad_hook=None):
+             sigmainv, boxlen_m, knum, ws, bins_valid, feature_grad_hook=None, views=None, out=None):
     """Calls dibr_b200_backward; returns (grad_face_vertices_image, grad_face_features fp32).
+
+    ``views=(v0, v1)`` restricts the call to those views of the batch (dibr_b200_backward_views: all
+    tensors stay the full-batch ones, only rows v0..v1-1 of the gradients are written) and ``out=
+    (g_fvi, g_ff)`` supplies the full-batch gradient buffers to write into - together they let a
+    caller pipeline view chunks (kaolin_b200.multi_gpu.pipelined_backward_all_gather).
 
     ``feature_grad_hook`` (per call — there is no process-global state): called as
     ``hook(g_ff)`` between the two branches of a fused backward.  grad_face_features is
@@ -165,9 +179,12 @@ def backward(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multip
     dev = fvi.device
     B, F = fvi.shape[0], fvi.shape[1]
     D = 0 if ff is None else ff.shape[-1]
-    g_fvi = torch.empty_like(fvi)
-    # grad_face_features is accumulated (atomics) in fp32 whatever the storage type
-    g_ff = torch.empty(ff.shape, dtype=torch.float32, device=dev) if ff is not None else None
+    if out is not None:
+        g_fvi, g_ff = out
+    else:
+        g_fvi = torch.empty_like(fvi)
+        # grad_face_features is accumulated (atomics) in fp32 whatever the storage type
+        g_ff = torch.empty(ff.shape, dtype=torch.float32, device=dev) if ff is not None else None
     # The workspace carries forward's bins / hit cache (soft-mask branch, bins_valid) and the
     # per-face records of the row-walk rasterize backward; without forward state a fresh
     # minimum-size one serves both.
@@ -180,11 +197,11 @@ def backward(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multip
     if hook is not None and g_feat is not None and g_soft is not None and D > 0:
         # two calls: rasterize branch (g_ff final -> hook), then the soft-mask branch added on top
         _backward_call(B, F, height, width, D, g_feat, None, face_idx, wts, None, fvi, ff, multiplier, eps,
-                       sigmainv, boxlen_m, knum, g_fvi, g_ff, ws, ws_bytes, 0, dev)
+                       sigmainv, boxlen_m, knum, g_fvi, g_ff, ws, ws_bytes, 0, dev, views)
         hook(g_ff)
         _backward_call(B, F, height, width, D, None, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps,
-                       sigmainv, boxlen_m, knum, g_fvi, None, ws, ws_bytes, flags | _lib.ACCUMULATE, dev)
+                       sigmainv, boxlen_m, knum, g_fvi, None, ws, ws_bytes, flags | _lib.ACCUMULATE, dev, views)
     else:
         _backward_call(B, F, height, width, D, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps,
-                       sigmainv, boxlen_m, knum, g_fvi, g_ff, ws, ws_bytes, flags, dev)
+                       sigmainv, boxlen_m, knum, g_fvi, g_ff, ws, ws_bytes, flags, dev, views)
     return g_fvi, g_ff

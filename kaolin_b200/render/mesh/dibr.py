@@ -92,6 +92,17 @@ class DibrRasterizationB200(Function):
         height, width, multiplier, eps, sigmainv, boxlen_m, knum = ctx.params
         g_feat = None if grad_features is None else grad_features.contiguous()
         g_soft = None if grad_soft_mask is None else grad_soft_mask.contiguous()
+        pipe = getattr(ctx, "view_pipeline", None)      # set on this node by PipelinedGradAllGather.attach
+        if pipe is not None and g_feat is not None and g_soft is not None and ctx.ws is not None:
+            # backward in view chunks; the exchange of chunk i travels while chunk i+1 computes
+            g_fvi = torch.empty_like(fvi)
+            g_ff = torch.empty(ff.shape, dtype=torch.float32, device=ff.device)
+
+            def run_chunk(c0, c1, hook):
+                _host.backward(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps, sigmainv,
+                               boxlen_m, knum, ctx.ws, True, feature_grad_hook=hook, views=(c0, c1), out=(g_fvi, g_ff))
+            pipe(fvi.shape[0], run_chunk, g_fvi, g_ff)
+            return None, None, None, g_fvi, g_ff.to(ff.dtype), None, None, None, None, None, None, None
         # per-node hook (set on this node by OverlappedGradAllGather.attach, never global)
         g_fvi, g_ff = _host.backward(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff,
                                      multiplier, eps, sigmainv, boxlen_m, knum, ctx.ws, ctx.ws is not None,

@@ -16,8 +16,8 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from kaolin_b200 import synthetic                                            # noqa: E402
-from kaolin_b200.multi_gpu import (ChunkedGradAllGather, OverlappedGradAllGather, chunk_ranges,  # noqa: E402
-                                   shard_range)
+from kaolin_b200.multi_gpu import (ChunkedGradAllGather, OverlappedGradAllGather, PipelinedGradAllGather,  # noqa: E402
+                                   chunk_ranges, shard_range)
 from kaolin_b200.render.mesh import dibr_rasterization                       # noqa: E402
 
 
@@ -49,13 +49,18 @@ def main():
     s0, s1 = shard_range(B, rank, world)
     out = {"rank": rank, "world": world, "views": [s0, s1]}
     ok = True
-    for mode in ("overlapped", "chunked"):
+    for mode in ("overlapped", "pipelined", "chunked"):
         l_fvi, l_ff = T(fvi[s0:s1]).requires_grad_(True), T(ff[s0:s1]).requires_grad_(True)
-        if mode == "overlapped":
+        if mode in ("overlapped", "pipelined"):
             feat, soft, idx = dibr_rasterization(H, W, T(fvz[s0:s1]), l_fvi, l_ff, T(fnz[s0:s1]))
-            gather = OverlappedGradAllGather(B).attach(soft)
-            torch.autograd.backward([feat, soft], [g_feat[s0:s1], g_soft[s0:s1]])
-            g_fvi, g_ff = gather.finish(l_fvi.grad, l_ff.grad)
+            if mode == "overlapped":
+                gather = OverlappedGradAllGather(B).attach(soft)
+                torch.autograd.backward([feat, soft], [g_feat[s0:s1], g_soft[s0:s1]])
+                g_fvi, g_ff = gather.finish(l_fvi.grad, l_ff.grad)
+            else:
+                gather = PipelinedGradAllGather(chunks=2).attach(soft)
+                torch.autograd.backward([feat, soft], [g_feat[s0:s1], g_soft[s0:s1]])
+                g_fvi, g_ff = gather.finish()
             same = (torch.equal(idx, full["idx"][s0:s1]) and torch.equal(soft, full["soft"][s0:s1])
                     and torch.equal(feat, full["feat"][s0:s1]))
         else:

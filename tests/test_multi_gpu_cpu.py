@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from kaolin_b200.multi_gpu import (shard_range, shard_views, all_gather_view_grads, chunk_ranges,
+from kaolin_b200.multi_gpu import (pipelined_backward_all_gather, shard_range, shard_views, all_gather_view_grads, chunk_ranges,
                                    ChunkedGradAllGather, OverlappedGradAllGather)
 
 
@@ -116,4 +116,32 @@ def test_two_rank_gloo_overlapped_gather():
     ok = mp.get_context("spawn").Array("i", [0, 0])
     port = 33500 + (os.getpid() % 2000)
     mp.spawn(_overlap_worker, args=(2, 6, port, ok), nprocs=2, join=True)
+    assert list(ok) == [1, 1]
+
+
+def _pipelined_worker(rank, world, batch, chunks, port, ok):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        g, f = _fake_grads(batch, 5)
+        lg, lf = shard_views([g, f], rank, world)
+        n = lg.shape[0]
+        g_fvi, g_ff = torch.zeros_like(lg), torch.zeros_like(lf)
+        order = []
+
+        def run_chunk(c0, c1, hook):            # what _host.backward(views=(c0, c1), out=..., feature_grad_hook=hook) does
+            g_ff[c0:c1] = lf[c0:c1]; order.append(("ff", c0)); hook(g_ff)
+            g_fvi[c0:c1] = lg[c0:c1]; order.append(("fvi", c0))
+        full_g, full_f = pipelined_backward_all_gather(n, chunks, run_chunk, g_fvi, g_ff)
+        ok[rank] = int(torch.equal(full_g, g) and torch.equal(full_f, f) and len(order) == 2 * min(chunks, n))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("batch,chunks", [(8, 2), (6, 3), (4, 1)])
+def test_two_rank_gloo_pipelined_backward_gather(batch, chunks):
+    ok = mp.get_context("spawn").Array("i", [0, 0])
+    port = 35500 + (os.getpid() % 2000) + batch * 8 + chunks
+    mp.spawn(_pipelined_worker, args=(2, batch, chunks, port, ok), nprocs=2, join=True)
     assert list(ok) == [1, 1]

@@ -35,6 +35,6 @@ def test_sharded_nccl_equals_single_gpu():
     assert r.returncode == 0, r.stderr[-2000:]
     assert len(results) == world and all(x["ok"] for x in results)
     for x in results:
-        for mode in ("overlapped", "chunked"):
+        for mode in ("overlapped", "pipelined", "chunked"):
             assert x[mode]["images_bit_equal"]
             assert x[mode]["grad_fvi_rel"] <= 1e-5 and x[mode]["grad_ff_rel"] <= 1e-5

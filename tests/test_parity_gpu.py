@@ -662,3 +662,33 @@ def test_graphed_fast_path_equals_eager():
         torch.autograd.backward([feat2, soft2], [g_feat, g_soft])
         assert torch.equal(idx, idx2) and torch.equal(soft, soft2) and torch.equal(feat, feat2)
         assert rel_err(N(a_fvi.grad), N(b_fvi.grad)) <= 1e-6 and rel_err(N(a_ff.grad), N(b_ff.grad)) <= 1e-6
+
+
+@pytest.mark.parametrize("variant", ["rows", "warp", "bf16"])
+def test_view_chunked_backward_equals_full_backward(variant, monkeypatch):
+    """dibr_b200_backward_views: the backward of views [0,2), [2,5) written into shared full-batch buffers
+    (with the feature-gradient hook between the branches) equals one full backward."""
+    from kaolin_b200.render.mesh import _host
+    if variant == "warp":
+        monkeypatch.setenv("DIBR_B200_RASTER_BWD", "warp")
+    fvz, fvi, fnz = synthetic.icosphere_views(5, 4, seed=71)
+    B, F = fvz.shape[:2]
+    H, W = 144, 160
+    dt = torch.bfloat16 if variant == "bf16" else torch.float32
+    ff = T(synthetic.random_features(B, F, 3, seed=72)).to(dt)
+    gen = torch.Generator(device=DEV); gen.manual_seed(73)
+    g_feat = torch.rand((B, H, W, 3), device=DEV, generator=gen).to(dt)
+    g_soft = torch.rand((B, H, W), device=DEV, generator=gen)
+    t_fvz, t_fvi, t_fnz = T(fvz), T(fvi), T(fnz)
+    feat, idx, wts, soft, ws = _host.forward(3, H, W, t_fvz, t_fvi, ff, t_fnz, None, 1000., 1e-8, 7000., 20., 30)
+    ref_fvi, ref_ff = _host.backward(H, W, g_feat, g_soft, idx, wts, soft, t_fvi, ff, 1000., 1e-8, 7000., 20., 30, ws, True)
+    g_fvi = torch.full_like(t_fvi, float("nan"))
+    g_ff = torch.full(ff.shape, float("nan"), dtype=torch.float32, device=DEV)
+    hooks = []
+    for c0, c1 in ((0, 2), (2, 5)):
+        _host.backward(H, W, g_feat, g_soft, idx, wts, soft, t_fvi, ff, 1000., 1e-8, 7000., 20., 30, ws, True,
+                       feature_grad_hook=lambda g, c0=c0, c1=c1: hooks.append(g[c0:c1].clone()),
+                       views=(c0, c1), out=(g_fvi, g_ff))
+        assert torch.isnan(g_fvi[c1:]).all() and not torch.isnan(g_fvi[:c1]).any()   # only these views were written
+    assert rel_err(N(g_fvi), N(ref_fvi)) <= 1e-6 and rel_err(N(g_ff), N(ref_ff)) <= 1e-6
+    assert rel_err(N(torch.cat(hooks)), N(ref_ff)) <= 1e-6          # g_ff was final at each hook
