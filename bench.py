@@ -73,6 +73,12 @@ def parse():
                         "travel while chunk i+1 computes. Default 1 (the feature gradient's gather overlaps the "
                         "soft-mask branch): measured at N = 2, two chunks cost +0.15 ms of backward compute "
                         "(half-size launches) for at most 0.1 ms of hidden exchange at N = 8")
+    p.add_argument("--gather", default="auto", choices=["auto", "nccl", "peer", "peer_sm"],
+                   help="N > 1: transport of the gradient all-gather. peer = stores into the peers' memory over "
+                        "NVLink by the copy engines (kaolin_b200.multi_gpu.PeerGradAllGather), peer_sm = the same by "
+                        "the dibr_b200_peer_push kernel, nccl = all_gather_into_tensor; auto = peer when CUDA "
+                        "symmetric memory can be set up on this box, else nccl")
+    p.add_argument("--push-ctas", type=int, default=32, help="--gather peer_sm: grid of the push kernel")
     p.add_argument("--chunks", type=int, default=1,
                    help="N > 1: 1 = the all-gather of grad_face_features overlaps the soft-mask branch of "
                         "the backward (default); k > 1 = k view-chunks per step, chunk i's all-gather "
@@ -265,8 +271,8 @@ def run_ours(args):
     import torch.distributed as dist
     from kaolin_b200 import _lib
     from kaolin_b200.render.mesh import _host, dibr_rasterization
-    from kaolin_b200.multi_gpu import (ChunkedGradAllGather, OverlappedGradAllGather, PipelinedGradAllGather,
-                                       chunk_ranges, pipelined_backward_all_gather)
+    from kaolin_b200.multi_gpu import (ChunkedGradAllGather, PipelinedGradAllGather, chunk_ranges,
+                                       make_grad_all_gather, pipelined_backward_all_gather)
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -316,6 +322,20 @@ def run_ours(args):
     bwd_chunks = args.bwd_chunks if args.bwd_chunks is not None else 1
     pipelined = world > 1 and len(spans) == 1 and bwd_chunks > 1
 
+    # transport of the exchange, decided once (collectively) before the warm-up
+    transport = {"used": None}
+
+    def new_gather():
+        g, used = make_grad_all_gather(B * world, (B, F, 3, 2), (B, F, 3, D), dev,
+                                       transport=transport["used"] or args.gather, ctas=args.push_ctas)
+        transport["used"] = used
+        return g
+
+    if world > 1 and len(spans) == 1 and not pipelined:
+        new_gather()
+        if rank == 0:
+            print(f"[bench] gradient all-gather transport: {transport['used']}", file=sys.stderr)
+
     def step_resident(ev=None):
         chunked = ChunkedGradAllGather(B) if world > 1 and len(spans) > 1 else None
         for ci, (c0, c1) in enumerate(spans):
@@ -335,7 +355,7 @@ def run_ours(args):
                 g_fvi, g_ff = pipelined_backward_all_gather(B, bwd_chunks, run, l_fvi, l_ff)
                 if ev: ev[3 * ci + 2].record()
             elif world > 1 and chunked is None:
-                gather = OverlappedGradAllGather(B * world)
+                gather = new_gather()
                 g_fvi, g_ff = bwd(gather.hook)
                 if ev: ev[3 * ci + 2].record()
                 g_fvi, g_ff = gather.finish(g_fvi)
@@ -484,7 +504,7 @@ def run_ours(args):
                 torch.autograd.backward([feat, soft], [g_feat, g_soft])
                 full = gather.finish()
             else:
-                gather = OverlappedGradAllGather(B * world).attach(soft)
+                gather = new_gather().attach(soft)
                 torch.autograd.backward([feat, soft], [g_feat, g_soft])
                 full = gather.finish(a_fvi.grad, a_ff.grad)
             g1, g2 = full[0][rank * B:(rank + 1) * B], full[1][rank * B:(rank + 1) * B]
@@ -681,7 +701,11 @@ def run_ours(args):
                    "views_per_gpu": B, "faces_per_view": F, "height": H,
                    "width": W, "feat_dim": D, "features": args.features, "cuda_graph": bool(args.graph and world == 1), "knum": KNUM, "sigmainv": SIGMAINV,
                    "boxlen": BOXLEN, "covered_fraction": covered,
-                   "parallelism": (f"views sharded x{world}; NCCL all-gather of per-view grads, "
+                   "gather_transport": transport["used"] if world > 1 else None,
+                   "parallelism": (f"views sharded x{world}; all-gather of per-view grads "
+                                   + ({"peer": "by copy-engine stores into peer memory over NVLink (symmetric memory), ",
+                                       "peer_sm": "by the dibr_b200_peer_push store kernel into peer memory over NVLink, "}
+                                      .get(transport["used"], "with NCCL, "))
                                    + (f"backward in {bwd_chunks} view chunks, chunk i's gathers overlap chunk i+1"
                                       if pipelined else
                                       "grad_face_features' gather overlapped with the soft-mask backward"

@@ -141,6 +141,34 @@ int dibr_b200_backward_views(
     dibr_b200_stream_t stream);
 
 /*
+ * float64 instantiation of the fused entry points (the reference dispatches float and double:
+ * rasterization_cuda.cu:218/427, dibr_soft_mask_cuda.cu:205/376; its tests parametrise the dtype).
+ * Same contract as dibr_b200_forward / dibr_b200_backward with double tensors (face_idx stays i64;
+ * multiplier / eps / sigmainv are C floats exactly as in the reference kernels' signatures, the
+ * enlarged-bbox margin boxlen * multiplier is a double as in dibr.py:33-39).  Every per-pixel decision
+ * is taken with the reference's <double> arithmetic (pixel centres computed in float and widened);
+ * built for exactness, not speed (one thread per pixel walks its tile's bins; double atomics in the
+ * backward).  workspace >= dibr_b200_workspace_bytes_f64(); pass it unchanged to the backward with
+ * DIBR_B200_BINS_VALID to reuse the forward's bins.
+ */
+size_t dibr_b200_workspace_bytes_f64(int batch, int64_t total_faces, int height, int width);
+int dibr_b200_forward_f64(
+    int batch, int num_faces, int height, int width, int feat_dim,
+    const double* face_vertices_z, const double* face_vertices_image,
+    const double* face_features, const double* face_normals_z, const uint8_t* valid_faces,
+    float multiplier, float eps, int mode, float sigmainv, double boxlen_m, int knum,
+    double* interpolated_features, int64_t* face_idx, double* output_weights, double* soft_mask,
+    void* workspace, size_t workspace_bytes, dibr_b200_stream_t stream);
+int dibr_b200_backward_f64(
+    int batch, int num_faces, int height, int width, int feat_dim,
+    const double* grad_features, const double* grad_soft_mask,
+    const int64_t* face_idx, const double* output_weights, const double* soft_mask,
+    const double* face_vertices_image, const double* face_features,
+    float multiplier, float eps, float sigmainv, double boxlen_m, int knum,
+    double* grad_face_vertices_image, double* grad_face_features,
+    void* workspace, size_t workspace_bytes, int flags, dibr_b200_stream_t stream);
+
+/*
  * bf16 feature storage (BASELINE.json configs[3], "bf16 features"; an extension - the
  * reference dispatches float/double only, rasterization_cuda.cu:218): same as
  * dibr_b200_forward / dibr_b200_backward except that face_features (B,F,3,D),
@@ -315,6 +343,19 @@ int dibr_b200_deftet_sparse_render_backward(
     const float* grad_interpolated_features, const int64_t* face_idx, const float* weights,
     const float* face_vertices_image, const float* face_features, float eps,
     float* grad_face_vertices_image, float* grad_face_features, dibr_b200_stream_t stream);
+
+/*
+ * Exchange step of the view-sharded path (kaolin_b200/csrc/peer_push.cu): the
+ * reference has no multi-GPU code - its callers all-gather the per-view gradients with
+ * torch.distributed.  All-gather by STORES over NVLink: copies `bytes` (multiple of 16) from the
+ * local device buffer `src` to dst[i] + dst_offset_bytes for i < n_dst (<= 16), where dst[i] are
+ * device pointers valid in this process (local memory or peer memory mapped through CUDA
+ * symmetric / IPC memory; host array of pointers).  `ctas` bounds the grid (<= 0: 32) so that the
+ * kernel can run underneath compute.  Asynchronous on `stream`; a cross-rank barrier after it is
+ * the caller's (kaolin_b200/multi_gpu.py:PeerGradAllGather).
+ */
+int dibr_b200_peer_push(const void* src, size_t bytes, void* const* dst, int n_dst, size_t dst_offset_bytes,
+                        int ctas, dibr_b200_stream_t stream);
 
 #ifdef __cplusplus
 }

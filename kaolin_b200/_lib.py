@@ -14,8 +14,9 @@ CSRC = os.path.join(_HERE, "csrc")
 # DIBR_B200_LIB: an alternative build of the same sources (A/B experiments on the GPU box only)
 LIB_PATH = os.environ.get("DIBR_B200_LIB") or os.path.join(CSRC, "libdibr_b200.so")
 SOURCES = [os.path.join(CSRC, "dibr_b200.cu"), os.path.join(CSRC, "mesh_pipeline.cu"),
-           os.path.join(CSRC, "deftet.cu")]
-HEADERS = [os.path.join(CSRC, "dibr_math.cuh"),
+           os.path.join(CSRC, "deftet.cu"), os.path.join(CSRC, "peer_push.cu")]
+HEADERS = [os.path.join(CSRC, "dibr_math.cuh"), os.path.join(CSRC, "dibr_math_f64.cuh"),
+           os.path.join(CSRC, "dibr_f64.cuh"),
            os.path.join(_HERE, "..", "include", "dibr_b200.h")]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]
@@ -31,12 +32,14 @@ _vp = ctypes.c_void_p
 _i = ctypes.c_int
 _i64 = ctypes.c_int64
 _f = ctypes.c_float
+_d = ctypes.c_double
 _sz = ctypes.c_size_t
 _fp3 = ctypes.POINTER(ctypes.c_float)      # HOST pointer to 3 floats (camera_proj)
 
 SIGNATURES = {
     "dibr_b200_version": (_i, []),
     "dibr_b200_trace_begin": (_i, []),
+    "dibr_b200_peer_push": (_i, [_vp, _sz, ctypes.POINTER(ctypes.c_void_p), _i, _sz, _i, _vp]),
     "dibr_b200_trace_end": (_i, [ctypes.c_char_p, _sz, ctypes.POINTER(ctypes.c_float), _i]),
     "dibr_b200_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "dibr_b200_workspace_bytes_cached": (_sz, [_i, _i64, _i, _i, _i, _i64]),
@@ -46,6 +49,11 @@ SIGNATURES = {
                                 _f, _f, _f, _f, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "dibr_b200_backward_views": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i,
                                       _f, _f, _f, _f, _i, _vp, _vp, _vp, _sz, _i, _i, _i, _vp]),
+    "dibr_b200_workspace_bytes_f64": (_sz, [_i, _i64, _i, _i]),
+    "dibr_b200_forward_f64": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _f, _d, _i,
+                                   _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "dibr_b200_backward_f64": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,
+                                    _f, _f, _f, _d, _i, _vp, _vp, _vp, _sz, _i, _vp]),
     "dibr_b200_forward_bf16": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _f, _f, _i, _f, _f, _i,
                                     _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "dibr_b200_backward_bf16": (_i, [_i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp,

@@ -2758,10 +2758,84 @@ int launch_raster_bwd_rows(const RasterBwdArgs& r, float* acc, int accumulate_xy
   }
 }
 
+#include "dibr_f64.cuh"
+
 }  // namespace
 
 // ===========================================================================
 extern "C" {
+
+size_t dibr_b200_workspace_bytes_f64(int batch, int64_t total_faces, int height, int width) {
+  if (check_dims(batch, total_faces, height, width)) return 0;
+  return f64_layout(batch, total_faces, height, width).total;
+}
+
+int dibr_b200_forward_f64(int batch, int num_faces, int height, int width, int feat_dim,
+                          const double* face_vertices_z, const double* face_vertices_image,
+                          const double* face_features, const double* face_normals_z, const uint8_t* valid_faces,
+                          float multiplier, float eps, int mode, float sigmainv, double boxlen_m, int knum,
+                          double* interpolated_features, int64_t* face_idx, double* output_weights,
+                          double* soft_mask, void* workspace, size_t workspace_bytes_, dibr_b200_stream_t stream) {
+  const int64_t NF = (int64_t)batch * num_faces;
+  int rc = check_dims(batch, NF, height, width);
+  if (rc) return rc;
+  const bool raster = mode & DIBR_B200_RASTER, soft = mode & DIBR_B200_SOFT_MASK;
+  if ((!raster && !soft) || num_faces < 0 || feat_dim < 0 || !face_idx || !(multiplier > 0.f)) return DIBR_B200_EINVAL;
+  if (num_faces > 0 && !face_vertices_image) return DIBR_B200_EINVAL;
+  if (raster && (!output_weights || (feat_dim > 0 && (!interpolated_features || (num_faces > 0 && !face_features))) ||
+                 (num_faces > 0 && !face_vertices_z)))
+    return DIBR_B200_EINVAL;
+  if (soft && (!soft_mask || knum <= 0)) return DIBR_B200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  F64Args a;
+  rc = f64_setup(a, batch, num_faces, height, width, face_vertices_image, face_normals_z, valid_faces, multiplier,
+                 boxlen_m, (raster ? 1 : 0) | (soft ? 2 : 0), true, workspace, workspace_bytes_, st);
+  if (rc) return rc;
+  a.D = feat_dim; a.K = knum; a.mode = mode; a.eps = eps; a.sigmainv = sigmainv; a.multiplier = multiplier;
+  a.margin = boxlen_m; a.xy = face_vertices_image; a.z = face_vertices_z; a.feat = face_features;
+  a.out_feat = interpolated_features; a.idx = face_idx; a.out_w = output_weights; a.out_soft = soft_mask;
+  a.g_feat = nullptr; a.g_soft = nullptr; a.soft = nullptr; a.g_xy = nullptr; a.g_ff = nullptr;
+  Span sp("dibr_f64_kernel<forward>", st);
+  dibr_f64_kernel<false><<<tile_grid(a.s), kThreads, 0, st>>>(a);
+  return (int)cudaGetLastError();
+}
+
+int dibr_b200_backward_f64(int batch, int num_faces, int height, int width, int feat_dim,
+                           const double* grad_features, const double* grad_soft_mask, const int64_t* face_idx,
+                           const double* output_weights, const double* soft_mask, const double* face_vertices_image,
+                           const double* face_features, float multiplier, float eps, float sigmainv, double boxlen_m,
+                           int knum, double* grad_face_vertices_image, double* grad_face_features, void* workspace,
+                           size_t workspace_bytes_, int flags, dibr_b200_stream_t stream) {
+  const int64_t NF = (int64_t)batch * num_faces;
+  int rc = check_dims(batch, NF, height, width);
+  if (rc) return rc;
+  if (!face_idx || !grad_face_vertices_image || num_faces < 0 || feat_dim < 0 || !(multiplier > 0.f)) return DIBR_B200_EINVAL;
+  if (num_faces > 0 && !face_vertices_image) return DIBR_B200_EINVAL;
+  const bool run_raster = grad_features && feat_dim > 0;
+  if (run_raster && NF > 0 && (!output_weights || !face_features || !grad_face_features)) return DIBR_B200_EINVAL;
+  if (grad_soft_mask && (!soft_mask || knum <= 0)) return DIBR_B200_EINVAL;
+  cudaStream_t st = (cudaStream_t)stream;
+  cudaError_t e = cudaMemsetAsync(grad_face_vertices_image, 0, (size_t)NF * 6 * sizeof(double), st);
+  if (e != cudaSuccess) return (int)e;
+  if (grad_face_features && feat_dim > 0) {
+    e = cudaMemsetAsync(grad_face_features, 0, (size_t)NF * 3 * feat_dim * sizeof(double), st);
+    if (e != cudaSuccess) return (int)e;
+  }
+  if (NF == 0 || (!run_raster && !grad_soft_mask)) return 0;
+  F64Args a;
+  // the soft-mask branch needs the enlarged bins: forward's (BINS_VALID) or rebuilt here
+  rc = f64_setup(a, batch, num_faces, height, width, face_vertices_image, nullptr, nullptr, multiplier, boxlen_m, 2,
+                 grad_soft_mask && !(flags & DIBR_B200_BINS_VALID), workspace, workspace_bytes_, st);
+  if (rc) return rc;
+  a.D = feat_dim; a.K = knum; a.mode = 0; a.eps = eps; a.sigmainv = sigmainv; a.multiplier = multiplier;
+  a.margin = boxlen_m; a.xy = face_vertices_image; a.z = nullptr; a.feat = face_features;
+  a.out_feat = nullptr; a.idx = const_cast<int64_t*>(face_idx); a.out_w = const_cast<double*>(output_weights);
+  a.out_soft = nullptr; a.g_feat = run_raster ? grad_features : nullptr; a.g_soft = grad_soft_mask; a.soft = soft_mask;
+  a.g_xy = grad_face_vertices_image; a.g_ff = grad_face_features;
+  Span sp("dibr_f64_kernel<backward>", st);
+  dibr_f64_kernel<true><<<tile_grid(a.s), kThreads, 0, st>>>(a);
+  return (int)cudaGetLastError();
+}
 
 int dibr_b200_trace_begin(void) {
   g_trace.on = true;
@@ -2822,7 +2896,7 @@ static int forward_impl(int batch, int num_faces, int height, int width, int fea
   const bool raster = mode & DIBR_B200_RASTER, soft = mode & DIBR_B200_SOFT_MASK;
   if ((!raster && !soft) || num_faces < 0 || feat_dim < 0 || !face_idx) return DIBR_B200_EINVAL;
   if (num_faces > 0 && !face_vertices_image) return DIBR_B200_EINVAL;
-  if (raster && (!output_weights || (feat_dim > 0 && (!interpolated_features || !face_features)) ||
+  if (raster && (!output_weights || (feat_dim > 0 && (!interpolated_features || (num_faces > 0 && !face_features))) ||
                  (num_faces > 0 && !face_vertices_z)))
     return DIBR_B200_EINVAL;
   if (soft && (!soft_mask || knum <= 0)) return DIBR_B200_EINVAL;
@@ -3023,7 +3097,7 @@ int dibr_b200_packed_rasterize_forward(int batch, int64_t total_faces, int heigh
   int rc = check_dims(batch, total_faces, height, width);
   if (rc) return rc;
   if (!selected_face_idx || !output_weights || !first_idx_face_per_mesh || feat_dim < 0) return DIBR_B200_EINVAL;
-  if (feat_dim > 0 && (!interpolated_features || !face_features)) return DIBR_B200_EINVAL;
+  if (feat_dim > 0 && (!interpolated_features || (total_faces > 0 && !face_features))) return DIBR_B200_EINVAL;
   if (total_faces > 0 && (!face_vertices_z || !face_vertices_image || !face_bboxes)) return DIBR_B200_EINVAL;
   cudaStream_t st = (cudaStream_t)stream;
   FwdArgs a;

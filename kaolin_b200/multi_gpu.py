@@ -17,7 +17,7 @@ import torch.distributed as dist
 
 __all__ = ["shard_range", "shard_views", "all_gather_view_grads", "chunk_ranges",
            "ChunkedGradAllGather", "OverlappedGradAllGather", "pipelined_backward_all_gather",
-           "PipelinedGradAllGather"]
+           "PipelinedGradAllGather", "PeerGradAllGather", "make_grad_all_gather"]
 
 
 def shard_range(batch, rank, world_size):
@@ -258,3 +258,210 @@ class PipelinedGradAllGather:
             raise RuntimeError("the attached backward has not run (both output gradients are needed)")
         out, self.result = self.result, None
         return out
+
+
+# ---------------------------------------------------------------------------
+# All-gather by stores into peer memory (NVLink / NVSwitch)
+class _PeerPool:
+    """Symmetric landing buffers of one (group, gradient shapes) configuration, mapped into every
+    rank of the box (``torch.distributed._symmetric_memory``: CUDA VMM allocations exchanged
+    between the processes; ``buffer_ptrs[r]`` is rank r's buffer as a pointer valid HERE), two
+    generations of them, plus the side streams the pushes run on.  Created once (the rendezvous is
+    a collective and costs milliseconds) and reused by every step."""
+
+    def __init__(self, group, device, local_views, shape_fvi, shape_ff, dtype, n_streams):
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = group if group is not None else dist.group.WORLD
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+        self.device = device
+        self.local_views = local_views
+        self.shapes = {"fvi": (local_views,) + tuple(shape_fvi), "ff": (local_views,) + tuple(shape_ff)}
+        self.dtype = dtype
+        esz = torch.empty((), dtype=dtype).element_size()
+        self.numel = {k: int(torch.Size(v).numel()) for k, v in self.shapes.items()}
+        for k, n in self.numel.items():
+            if (n * esz) % 16:
+                raise ValueError(f"PeerGradAllGather: the {k} shard is {n * esz} bytes, not a multiple of 16")
+        # layout of one generation: [world][fvi shard] then [world][ff shard]; two generations
+        self.off = {"fvi": 0, "ff": self.world * self.numel["fvi"]}
+        self.gen_numel = self.world * (self.numel["fvi"] + self.numel["ff"])
+        self.buf = symm_mem.empty(2 * self.gen_numel, dtype=dtype, device=device)
+        self.hdl = symm_mem.rendezvous(self.buf, self.group)
+        self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.esz = esz
+        self.streams = [torch.cuda.Stream(device, priority=-1) for _ in range(max(1, int(n_streams)))]
+        self.generation = 0
+        self._views = {}
+
+    def landing(self, owner, gen, kind, src_rank=None):
+        """Tensor view of rank `owner`'s landing area for `kind`: all ranks' slots, or `src_rank`'s."""
+        key = (owner, gen, kind, src_rank)
+        v = self._views.get(key)
+        if v is None:
+            n = self.numel[kind]
+            off = gen * self.gen_numel + self.off[kind]
+            if src_rank is None:
+                v = self.hdl.get_buffer(owner, (self.world,) + self.shapes[kind], self.dtype, off)
+            else:
+                v = self.hdl.get_buffer(owner, self.shapes[kind], self.dtype, off + src_rank * n)
+            self._views[key] = v
+        return v
+
+    def byte_offset(self, gen, kind, src_rank):
+        return (gen * self.gen_numel + self.off[kind] + src_rank * self.numel[kind]) * self.esz
+
+
+_peer_pools = {}
+
+
+class PeerGradAllGather:
+    """``OverlappedGradAllGather`` with the transfer done by STORES into the peers' memory over
+    NVLink instead of an NCCL collective: every rank pushes its ``grad_face_features`` shard into
+    slot `rank` of every peer's landing buffer as soon as the rasterize branch of the backward has
+    produced it (``hook``), and its ``grad_face_vertices_image`` shard at the end (``finish``).
+
+    ``engine="ce"``: one peer-to-peer ``copy_`` per destination on high-priority side streams - the
+    copy engines move the bytes, no SM is taken from the soft-mask branch that runs meanwhile.
+    ``engine="sm"``: ``dibr_b200_peer_push`` (csrc/peer_push.cu), one small kernel that loads each 16 B
+    of the shard once and stores it to all destinations.
+
+    Cross-rank ordering: ``finish`` ends with the symmetric-memory barrier on the side stream (every
+    rank's pushes are complete when it passes) and makes the current stream wait for it.  The
+    landing buffers are persistent and double-buffered: the tensors returned by ``finish`` stay
+    valid until the ``finish`` after the next one, provided they are consumed on the current stream
+    (a rank starts pushing generation g+2 only after its own consumer of generation g, which
+    precedes its next backward in stream order, and after every rank passed barrier g+1).
+    Same interface as ``OverlappedGradAllGather`` (``hook`` / ``attach`` / ``finish``); equal
+    shards, one box.  Raises at construction when symmetric memory is unavailable
+    (``make_grad_all_gather`` falls back to NCCL)."""
+
+    BARRIER_TIMEOUT_MS = 20000
+
+    def __init__(self, batch, local_fvi_shape, local_ff_shape, device, dtype=torch.float32, group=None,
+                 engine="ce", streams=4, ctas=32):
+        self.world = dist.get_world_size(group)
+        if batch % self.world:
+            raise ValueError(f"batch {batch} is not divisible by the world size {self.world}")
+        if engine not in ("ce", "sm"):
+            raise ValueError("engine must be 'ce' or 'sm'")
+        self.batch = int(batch)
+        self.engine = engine
+        self.ctas = int(ctas)
+        lv = self.batch // self.world
+        key = (id(group), str(device), lv, tuple(local_fvi_shape), tuple(local_ff_shape), dtype)
+        pool = _peer_pools.get(key)
+        if pool is None:
+            pool = _PeerPool(group, device, lv, tuple(local_fvi_shape)[1:], tuple(local_ff_shape)[1:], dtype, streams)
+            _peer_pools[key] = pool
+        self.pool = pool
+        self.gen = pool.generation
+        pool.generation ^= 1
+        self.keep = []
+        self.pushed_ff = False
+
+    def _push(self, kind, local):
+        pool = self.pool
+        if tuple(local.shape) != pool.shapes[kind] or local.dtype != pool.dtype:
+            raise ValueError(f"PeerGradAllGather: {kind} shard is {tuple(local.shape)} {local.dtype}, "
+                             f"expected {pool.shapes[kind]} {pool.dtype}")
+        local = local.contiguous()
+        self.keep.append(local)               # alive until finish(): the side streams read it
+        dev = pool.device
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(dev))
+        order = [(pool.rank + 1 + k) % pool.world for k in range(pool.world)]     # self last, peers rotated
+        if self.engine == "sm":
+            import ctypes
+            from . import _lib
+            s = pool.streams[0]
+            s.wait_event(ready)
+            arr = (ctypes.c_void_p * pool.world)(*[pool.ptrs[r] for r in order])
+            st = _lib.lib().dibr_b200_peer_push(ctypes.c_void_p(local.data_ptr()), local.numel() * pool.esz, arr,
+                                                pool.world, pool.byte_offset(self.gen, kind, pool.rank), self.ctas,
+                                                ctypes.c_void_p(s.cuda_stream))
+            _lib.check(st, "dibr_b200_peer_push")
+            return
+        for i, r in enumerate(order):
+            s = pool.streams[i % len(pool.streams)]
+            s.wait_event(ready)
+            with torch.cuda.stream(s):
+                pool.landing(r, self.gen, kind, pool.rank).copy_(local, non_blocking=True)
+
+    def hook(self, g_ff):
+        if self.pushed_ff:
+            raise RuntimeError("PeerGradAllGather covers one backward call")
+        self._push("ff", g_ff)
+        self.pushed_ff = True
+
+    def attach(self, output):
+        _dibr_node(output).feature_grad_hook = self.hook
+        return self
+
+    def finish(self, g_fvi, g_ff=None):
+        pool = self.pool
+        if not self.pushed_ff:
+            if g_ff is None:
+                raise RuntimeError("no feature gradient was produced by the attached backward and none was passed")
+            self._push("ff", g_ff)
+        self._push("fvi", g_fvi)
+        s0 = pool.streams[0]
+        for s in pool.streams[1:]:
+            e = torch.cuda.Event(); e.record(s); s0.wait_event(e)
+        with torch.cuda.stream(s0):
+            pool.hdl.barrier(channel=self.gen, timeout_ms=self.BARRIER_TIMEOUT_MS)
+        done = torch.cuda.Event(); done.record(s0)
+        torch.cuda.current_stream(pool.device).wait_event(done)
+        self.keep = []
+        full_fvi = pool.landing(pool.rank, self.gen, "fvi").reshape((self.batch,) + pool.shapes["fvi"][1:])
+        full_ff = pool.landing(pool.rank, self.gen, "ff").reshape((self.batch,) + pool.shapes["ff"][1:])
+        return full_fvi, full_ff
+
+
+def _dibr_node(output):
+    node = getattr(output, "grad_fn", None)
+    seen = 0
+    while node is not None and not type(node).__name__.startswith("DibrRasterizationB200") and seen < 4:
+        nxt = [fn for fn, _ in node.next_functions if fn is not None]
+        node = nxt[0] if len(nxt) == 1 else None
+        seen += 1
+    if node is None or not type(node).__name__.startswith("DibrRasterizationB200"):
+        raise ValueError("attach() needs an output of kaolin_b200.render.mesh.dibr_rasterization "
+                         "that requires grad")
+    return node
+
+
+def make_grad_all_gather(batch, local_fvi_shape, local_ff_shape, device, transport="auto", group=None, **kw):
+    """-> (gather, transport used).  ``transport``: "peer" / "peer_sm" (``PeerGradAllGather`` with the
+    copy-engine or the store-kernel engine; raises if symmetric memory cannot be set up), "nccl"
+    (``OverlappedGradAllGather``) or "auto" (peer when the device is CUDA and symmetric memory
+    works, else nccl - decided collectively so that all ranks take the same path)."""
+    if transport == "nccl":
+        return OverlappedGradAllGather(batch, group), "nccl"
+    engine = "sm" if transport == "peer_sm" else "ce"
+    if transport in ("peer", "peer_sm"):
+        return PeerGradAllGather(batch, local_fvi_shape, local_ff_shape, device, group=group, engine=engine, **kw), transport
+    if transport != "auto":
+        raise ValueError(f"unknown transport {transport!r}")
+    state = _auto_state.get(id(group))
+    if state is None:
+        ok, gather = 1, None
+        if torch.device(device).type != "cuda":
+            ok = 0
+        else:
+            try:
+                gather = PeerGradAllGather(batch, local_fvi_shape, local_ff_shape, device, group=group, **kw)
+            except Exception as exc:          # no symmetric memory on this system / in this container
+                ok = 0
+                _auto_state[("why", id(group))] = f"{type(exc).__name__}: {exc}"
+        flag = torch.tensor([ok], dtype=torch.int32, device=device if torch.device(device).type == "cuda" else "cpu")
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
+        state = _auto_state[id(group)] = "peer" if int(flag.item()) == 1 else "nccl"
+        if state == "peer" and gather is not None:
+            return gather, "peer"
+    if state == "peer":
+        return PeerGradAllGather(batch, local_fvi_shape, local_ff_shape, device, group=group, **kw), "peer"
+    return OverlappedGradAllGather(batch, group), "nccl"
+
+
+_auto_state = {}

@@ -42,32 +42,8 @@ def check_tensors(func, named, dtype=torch.float32):
             raise RuntimeError(f"{func}: expected all tensors on {dev}, {name} is on {t.device}")
         if dtype is not None and t.is_floating_point() and t.dtype != dtype:
             raise RuntimeError(f"\"{func}\" not implemented for '{str(t.dtype).replace('torch.', '')}' "
-                               "(kaolin_b200 supports float32)")
+                               "(kaolin_b200 supports float32 and float64)")
     return dev
-
-
-_warned_fp64 = []
-
-
-def wants_fp64(*tensors):
-    """True when the caller passed float64 geometry/features (the reference dispatches float and
-    double, rasterization_cuda.cu:218/427, dibr_soft_mask_cuda.cu:205/376).  kaolin_b200 has fp32
-    kernels only: float64 inputs are ACCEPTED, computed in float32 and the floating-point
-    outputs / gradients are returned as float64 (through differentiable casts), so a double
-    caller keeps working; results carry fp32 rounding (~1e-7 relative) and face_idx can differ
-    from the reference's double kernels at pixels where an fp32 rounding decides coverage or
-    depth order.  Warns once per process."""
-    hit = any(isinstance(t, torch.Tensor) and t.dtype == torch.float64 for t in tensors)
-    if hit and not _warned_fp64:
-        import warnings
-        _warned_fp64.append(True)
-        warnings.warn("kaolin_b200: float64 inputs are computed in float32 (fp32 kernels only); outputs and "
-                      "gradients are cast back to float64", stacklevel=3)
-    return hit
-
-
-def to_fp32(t):
-    return t.to(torch.float32) if isinstance(t, torch.Tensor) and t.dtype == torch.float64 else t
 
 
 def check_size(func, name, t, shape):
@@ -179,6 +155,8 @@ def backward(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multip
     dev = fvi.device
     B, F = fvi.shape[0], fvi.shape[1]
     D = 0 if ff is None else ff.shape[-1]
+    if B * F == 0 and out is None:       # empty mesh: empty gradients, nothing to launch
+        return torch.zeros_like(fvi), (torch.zeros(ff.shape, dtype=torch.float32, device=dev) if ff is not None else None)
     if out is not None:
         g_fvi, g_ff = out
     else:
@@ -204,4 +182,53 @@ def backward(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multip
     else:
         _backward_call(B, F, height, width, D, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps,
                        sigmainv, boxlen_m, knum, g_fvi, g_ff, ws, ws_bytes, flags, dev, views)
+    return g_fvi, g_ff
+
+
+# ---------------------------------------------------------------------------
+# float64 instantiation (dibr_b200_forward_f64 / dibr_b200_backward_f64)
+def forward_f64(mode, height, width, fvz, fvi, ff, fnz, valid_u8, multiplier, eps, sigmainv, boxlen_m, knum,
+                face_idx_in=None):
+    """-> (feat f64, face_idx, weights f64, soft f64, workspace); boxlen_m is a Python float (double)."""
+    dev = fvi.device
+    B, F = fvi.shape[0], fvi.shape[1]
+    D = 0 if ff is None else ff.shape[-1]
+    raster = bool(mode & _lib.RASTER)
+    soft_on = bool(mode & _lib.SOFT_MASK)
+    f64 = torch.float64
+    feat = torch.empty((B, height, width, D), dtype=f64, device=dev) if raster else None
+    wts = torch.empty((B, height, width, 3), dtype=f64, device=dev) if raster else None
+    idx = torch.empty((B, height, width), dtype=torch.int64, device=dev) if raster else face_idx_in
+    soft = torch.empty((B, height, width), dtype=f64, device=dev) if soft_on else None
+    n = _lib.lib().dibr_b200_workspace_bytes_f64(B, B * F, height, width)
+    if n == 0:
+        raise RuntimeError("kaolin_b200: unsupported problem size")
+    ws = torch.empty(n, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().dibr_b200_forward_f64(
+            B, F, height, width, D, ptr(fvz), ptr(fvi), ptr(ff), ptr(fnz), ptr(valid_u8), float(multiplier),
+            float(eps), mode, float(sigmainv), float(boxlen_m), int(knum), ptr(feat), ptr(idx), ptr(wts), ptr(soft),
+            ptr(ws), ws.numel(), stream_ptr(dev))
+    _lib.check(st, "dibr_b200_forward_f64")
+    return feat, idx, wts, soft, ws
+
+
+def backward_f64(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps, sigmainv, boxlen_m,
+                 knum, ws):
+    dev = fvi.device
+    B, F = fvi.shape[0], fvi.shape[1]
+    D = 0 if ff is None else ff.shape[-1]
+    if B * F == 0:
+        return torch.zeros_like(fvi), (torch.zeros_like(ff) if ff is not None else None)
+    g_fvi = torch.empty_like(fvi)
+    g_ff = torch.empty_like(ff) if ff is not None else None
+    flags = _lib.BINS_VALID if ws is not None else 0
+    if ws is None:
+        ws = torch.empty(_lib.lib().dibr_b200_workspace_bytes_f64(B, B * F, height, width), dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        st = _lib.lib().dibr_b200_backward_f64(
+            B, F, height, width, D, ptr(g_feat), ptr(g_soft), ptr(face_idx), ptr(wts), ptr(soft), ptr(fvi), ptr(ff),
+            float(multiplier), float(eps), float(sigmainv), float(boxlen_m), int(knum), ptr(g_fvi), ptr(g_ff),
+            ptr(ws), ws.numel(), int(flags), stream_ptr(dev))
+    _lib.check(st, "dibr_b200_backward_f64")
     return g_fvi, g_ff

@@ -45,12 +45,97 @@ class DibrSoftMaskB200(Function):
         return g_fvi, None, None, None, None, None
 
 
+class DibrSoftMaskF64(Function):
+    """float64 instantiation of ``DibrSoftMaskCuda`` (dibr_b200_forward_f64, mode SOFT_MASK)."""
+
+    @staticmethod
+    def forward(ctx, face_vertices_image, selected_face_idx, sigmainv, boxlen, knum, multiplier):
+        fvi, idx = face_vertices_image.contiguous(), selected_face_idx.contiguous()
+        B, H, W = idx.shape
+        boxlen_m = boxlen * multiplier                                    # a Python float: double, as dibr.py:36-37
+        _, _, _, soft, ws = _host.forward_f64(_lib.SOFT_MASK, H, W, None, fvi, None, None, None, multiplier, 0.,
+                                              sigmainv, boxlen_m, knum, face_idx_in=idx)
+        ctx.save_for_backward(soft, fvi, idx)
+        ctx.params = (sigmainv, boxlen_m, knum, multiplier)
+        ctx.ws = ws if ctx.needs_input_grad[0] else None
+        return soft
+
+    @staticmethod
+    def backward(ctx, grad_soft_mask):
+        soft, fvi, idx = ctx.saved_tensors
+        sigmainv, boxlen_m, knum, multiplier = ctx.params
+        B, H, W = idx.shape
+        g_fvi, _ = _host.backward_f64(H, W, None, grad_soft_mask.contiguous(), idx, None, soft, fvi, None, multiplier,
+                                      0., sigmainv, boxlen_m, knum, ctx.ws)
+        return g_fvi, None, None, None, None, None
+
+
+class DibrRasterizationF64(Function):
+    """float64 instantiation of the fused node (the reference's <double> kernels' arithmetic)."""
+
+    @staticmethod
+    def forward(ctx, height, width, fvz, fvi, ff, fnz, sigmainv, boxlen, knum, multiplier, eps, soft_multiplier):
+        fvz, fvi, ff, fnz = fvz.contiguous(), fvi.contiguous(), ff.contiguous(), fnz.contiguous()
+        boxlen_m = boxlen * soft_multiplier
+        feat, face_idx, wts, soft, ws = _host.forward_f64(_lib.RASTER | _lib.SOFT_MASK, height, width, fvz, fvi, ff,
+                                                          fnz, None, multiplier, eps, sigmainv, boxlen_m, knum)
+        ctx.save_for_backward(face_idx, wts, soft, fvi, ff)
+        ctx.mark_non_differentiable(face_idx)
+        ctx.set_materialize_grads(False)
+        ctx.params = (height, width, multiplier, eps, sigmainv, boxlen_m, knum)
+        ctx.ws = ws if (ctx.needs_input_grad[3] or ctx.needs_input_grad[4]) else None
+        return feat, soft, face_idx
+
+    @staticmethod
+    def backward(ctx, grad_features, grad_soft_mask, grad_face_idx):
+        face_idx, wts, soft, fvi, ff = ctx.saved_tensors
+        height, width, multiplier, eps, sigmainv, boxlen_m, knum = ctx.params
+        g_feat = None if grad_features is None else grad_features.contiguous()
+        g_soft = None if grad_soft_mask is None else grad_soft_mask.contiguous()
+        g_fvi, g_ff = _host.backward_f64(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps,
+                                         sigmainv, boxlen_m, knum, ctx.ws)
+        return None, None, None, g_fvi, g_ff, None, None, None, None, None, None, None
+
+
+def _dibr_rasterization_f64(height, width, face_vertices_z, face_vertices_image, face_features, face_normals_z,
+                            sigmainv, boxlen, knum, multiplier, eps):
+    if multiplier is None:
+        multiplier, soft_multiplier = 1000, 1000.
+    else:
+        soft_multiplier = multiplier
+    if eps is None:
+        eps = 1e-8
+    is_list = isinstance(face_features, (list, tuple))
+    ff = torch.cat(face_features, dim=-1) if is_list else face_features
+    _host.check_tensors("dibr_rasterization", [("face_vertices_z", face_vertices_z),
+                                               ("face_vertices_image", face_vertices_image), ("face_features", ff),
+                                               ("face_normals_z", face_normals_z)], dtype=None)
+    if face_vertices_z.dim() != 3 or face_vertices_z.shape[-1] != 3:
+        raise RuntimeError("dibr_rasterization: face_vertices_z must be of shape (batch_size, num_faces, 3)")
+    B, F, _ = face_vertices_z.shape
+    _host.check_size("dibr_rasterization", "face_vertices_image", face_vertices_image, (B, F, 3, 2))
+    _host.check_size("dibr_rasterization", "face_features", ff, (B, F, 3, ff.shape[-1]))
+    _host.check_size("dibr_rasterization", "face_normals_z", face_normals_z, (B, F))
+    d = torch.float64
+    feat, soft, face_idx = DibrRasterizationF64.apply(
+        height, width, face_vertices_z.to(d), face_vertices_image.to(d), ff.to(d), face_normals_z.to(d),
+        sigmainv, boxlen, knum, multiplier, eps, soft_multiplier)
+    if is_list:
+        outs, cur = [], 0
+        for f in face_features:
+            outs.append(feat[..., cur:cur + f.shape[-1]])
+            cur += f.shape[-1]
+        feat = tuple(outs)
+    return feat, soft, face_idx
+
+
 def dibr_soft_mask(face_vertices_image, selected_face_idx, sigmainv=7000, boxlen=0.02,
                    knum=30, multiplier=1000.):
     r"""Soft mask of DIB-R (see kaolin.render.mesh.dibr_soft_mask, dibr.py:75-117)."""
-    if _host.wants_fp64(face_vertices_image):
-        return dibr_soft_mask(face_vertices_image.float(), selected_face_idx, sigmainv, boxlen, knum,
-                              multiplier).double()
+    if face_vertices_image.dtype == torch.float64:
+        _host.check_tensors("dibr_soft_mask", [("face_vertices_image", face_vertices_image),
+                                               ("selected_face_idx", selected_face_idx)], dtype=None)
+        return DibrSoftMaskF64.apply(face_vertices_image, selected_face_idx, sigmainv, boxlen, knum, multiplier)
     _host.check_tensors("dibr_soft_mask", [("face_vertices_image", face_vertices_image),
                                            ("selected_face_idx", selected_face_idx)])
     if face_vertices_image.dim() != 4 or tuple(face_vertices_image.shape[2:]) != (3, 2):
@@ -120,14 +205,10 @@ def dibr_rasterization(height, width, face_vertices_z, face_vertices_image, face
         raise ValueError(f'"{rast_backend}" is not a valid backend, '
                          'kaolin_b200 only provides ["cuda"]')
     flat = list(face_features) if isinstance(face_features, (list, tuple)) else [face_features]
-    if _host.wants_fp64(face_vertices_z, face_vertices_image, face_normals_z, *flat):
-        ff32 = [_host.to_fp32(x) for x in flat]
-        out, soft, face_idx = dibr_rasterization(
-            height, width, _host.to_fp32(face_vertices_z), _host.to_fp32(face_vertices_image),
-            ff32 if isinstance(face_features, (list, tuple)) else ff32[0], _host.to_fp32(face_normals_z),
-            sigmainv, boxlen, knum, multiplier, eps, rast_backend)
-        out = tuple(o.double() for o in out) if isinstance(out, tuple) else out.double()
-        return out, soft.double(), face_idx
+    if any(isinstance(t, torch.Tensor) and t.dtype == torch.float64
+           for t in (face_vertices_z, face_vertices_image, face_normals_z, *flat)):
+        return _dibr_rasterization_f64(height, width, face_vertices_z, face_vertices_image, face_features,
+                                       face_normals_z, sigmainv, boxlen, knum, multiplier, eps)
     if multiplier is None:
         multiplier = 1000
         soft_multiplier = 1000.          # dibr.py:200

@@ -47,6 +47,56 @@ class RasterizeB200(Function):
         return None, None, None, g_fvi, g_ff, None, None, None
 
 
+class RasterizeF64(Function):
+    """float64 instantiation of ``RasterizeCuda`` (the reference dispatches float and double):
+    dibr_b200_forward_f64 / dibr_b200_backward_f64, the reference's <double> arithmetic."""
+
+    @staticmethod
+    def forward(ctx, height, width, fvz, fvi, ff, valid_faces, multiplier, eps):
+        fvz, fvi, ff = fvz.contiguous(), fvi.contiguous(), ff.contiguous()
+        valid_u8 = None
+        if valid_faces is not None:
+            valid_u8 = valid_faces.contiguous()
+            valid_u8 = valid_u8.view(torch.uint8) if valid_u8.dtype == torch.bool else valid_u8.ne(0).view(torch.uint8)
+        feat, face_idx, wts, _, _ = _host.forward_f64(_lib.RASTER, height, width, fvz, fvi, ff, None, valid_u8,
+                                                      multiplier, eps, 0., 0., 0)
+        ctx.save_for_backward(face_idx, wts, fvi, ff)
+        ctx.mark_non_differentiable(face_idx)
+        ctx.args = (height, width, eps)
+        return feat, face_idx
+
+    @staticmethod
+    def backward(ctx, grad_interpolated_features, grad_face_idx):
+        face_idx, wts, fvi, ff = ctx.saved_tensors
+        height, width, eps = ctx.args
+        g_fvi, g_ff = _host.backward_f64(height, width, grad_interpolated_features.contiguous(), None, face_idx, wts,
+                                         None, fvi, ff, 1.0, eps, 0., 0., 0, None)
+        return None, None, None, g_fvi, g_ff, None, None, None
+
+
+def _rasterize_f64(height, width, face_vertices_z, face_vertices_image, face_features, valid_faces, multiplier, eps):
+    is_list = isinstance(face_features, (list, tuple))
+    ff = torch.cat(face_features, dim=-1) if is_list else face_features
+    d = torch.float64
+    tensors = [("face_vertices_z", face_vertices_z), ("face_vertices_image", face_vertices_image),
+               ("face_features", ff)]
+    _host.check_tensors("rasterize", tensors, dtype=None)
+    if face_vertices_z.dim() != 3 or face_vertices_z.shape[-1] != 3:
+        raise RuntimeError("rasterize: face_vertices_z must be of shape (batch_size, num_faces, 3)")
+    B, F, _ = face_vertices_z.shape
+    _host.check_size("rasterize", "face_vertices_image", face_vertices_image, (B, F, 3, 2))
+    _host.check_size("rasterize", "face_features", ff, (B, F, 3, ff.shape[-1]))
+    out, face_idx = RasterizeF64.apply(height, width, face_vertices_z.to(d), face_vertices_image.to(d), ff.to(d),
+                                       valid_faces, multiplier, eps)
+    if is_list:
+        outs, cur = [], 0
+        for f in face_features:
+            outs.append(out[..., cur:cur + f.shape[-1]])
+            cur += f.shape[-1]
+        out = tuple(outs)
+    return out, face_idx
+
+
 def _check_inputs(func, face_vertices_z, face_vertices_image, face_features):
     _host.check_tensors(func, [("face_vertices_z", face_vertices_z),
                                ("face_vertices_image", face_vertices_image)])
@@ -78,14 +128,10 @@ def rasterize(height, width, face_vertices_z, face_vertices_image, face_features
         raise ValueError(f'"{backend}" is not a valid backend, '
                          'kaolin_b200 only provides ["cuda"]')
     flat = list(face_features) if isinstance(face_features, (list, tuple)) else [face_features]
-    if _host.wants_fp64(face_vertices_z, face_vertices_image, *flat):
-        # float64 callers: fp32 kernels, differentiable casts both ways (see _host.wants_fp64)
-        ff32 = [_host.to_fp32(x) for x in flat]
-        out, face_idx = rasterize(height, width, _host.to_fp32(face_vertices_z), _host.to_fp32(face_vertices_image),
-                                  ff32 if isinstance(face_features, (list, tuple)) else ff32[0],
-                                  valid_faces, multiplier, eps, backend)
-        out = tuple(o.double() for o in out) if isinstance(out, tuple) else out.double()
-        return out, face_idx
+    if any(isinstance(t, torch.Tensor) and t.dtype == torch.float64
+           for t in (face_vertices_z, face_vertices_image, *flat)):
+        return _rasterize_f64(height, width, face_vertices_z, face_vertices_image, face_features, valid_faces,
+                              multiplier, eps)
     _face_features = torch.cat(face_features, dim=-1) \
         if isinstance(face_features, (list, tuple)) else face_features
     B, F = _check_inputs("rasterize", face_vertices_z, face_vertices_image, _face_features)

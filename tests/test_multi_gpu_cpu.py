@@ -119,6 +119,43 @@ def test_two_rank_gloo_overlapped_gather():
     assert list(ok) == [1, 1]
 
 
+def _factory_worker(rank, world, batch, port, ok):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from kaolin_b200.multi_gpu import make_grad_all_gather, PeerGradAllGather
+        g, f = _fake_grads(batch, 5)
+        lg, lf = shard_views([g, f], rank, world)
+        # on CPU tensors "auto" agrees (collectively) on the NCCL-style gather; asked twice: cached decision
+        for _ in range(2):
+            gather, used = make_grad_all_gather(batch, lg.shape, lf.shape, "cpu", transport="auto")
+            gather.hook(lf.clone())
+            full_g, full_f = gather.finish(lg.clone())
+            good = used == "nccl" and torch.equal(full_g, g) and torch.equal(full_f, f)
+        # an explicit peer transport without symmetric memory is an error, not a silent fallback
+        try:
+            PeerGradAllGather(batch, lg.shape, lf.shape, "cpu")
+            raised = False
+        except Exception:
+            raised = True
+        try:
+            make_grad_all_gather(batch, lg.shape, lf.shape, "cpu", transport="carrier pigeon")
+            bad = False
+        except ValueError:
+            bad = True
+        ok[rank] = int(good and raised and bad)
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gather_factory_falls_back_collectively():
+    ok = mp.get_context("spawn").Array("i", [0, 0])
+    port = 35500 + (os.getpid() % 2000)
+    mp.spawn(_factory_worker, args=(2, 6, port, ok), nprocs=2, join=True)
+    assert list(ok) == [1, 1]
+
+
 def _pipelined_worker(rank, world, batch, chunks, port, ok):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)

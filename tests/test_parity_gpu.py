@@ -587,6 +587,21 @@ def test_soft_mask_windowed_path_many_tiles():
     assert rel_err(N(t_fvi.grad), o_g) <= GRAD_REL
 
 
+def test_empty_mesh():
+    """No faces at all (the reference's kernels loop over zero faces: background everywhere)."""
+    z = lambda *s: torch.zeros(s, device=DEV).requires_grad_(True)
+    fvi, ff = z(2, 0, 3, 2), z(2, 0, 3, 3)
+    feat, soft, idx = dibr_rasterization(40, 56, z(2, 0, 3), fvi, ff, z(2, 0))
+    assert feat.shape == (2, 40, 56, 3) and soft.shape == (2, 40, 56) and idx.shape == (2, 40, 56)
+    assert (idx == -1).all() and (feat == 0).all() and (soft == 0).all()
+    (feat.sum() + soft.sum()).backward()
+    assert fvi.grad.shape == fvi.shape and ff.grad.shape == ff.shape
+    out, idx = rasterize(40, 56, z(2, 0, 3), z(2, 0, 3, 2), z(2, 0, 3, 1))
+    assert (idx == -1).all() and (out == 0).all()
+    soft = dibr_soft_mask(z(2, 0, 3, 2), idx)
+    assert (soft == 0).all()
+
+
 def test_errors_like_reference():
     fvz, fvi, fnz = synthetic.icosphere_views(1, 1, seed=1)
     ff = synthetic.random_features(1, fvz.shape[1], 2)
@@ -596,7 +611,7 @@ def test_errors_like_reference():
         dibr_rasterization(8, 8, T(fvz), T(fvi), T(ff), T(fnz), rast_backend="nvdiffrast_fwd")
     with pytest.raises(RuntimeError):   # CPU tensors: no CPU path (rasterization.cpp:95-102)
         rasterize(8, 8, torch.from_numpy(fvz), torch.from_numpy(fvi), torch.from_numpy(ff))
-    # float64 callers are served (fp32 kernels, outputs cast back): tests/test_reference_wrappers.py
+    # float64 callers are served by the <double> instantiation: tests/test_f64_gpu.py
     out64, _ = rasterize(8, 8, T(fvz).double(), T(fvi).double(), T(ff).double())
     assert out64.dtype == torch.float64
     with pytest.raises(RuntimeError):   # half precision geometry is not a reference dtype either
