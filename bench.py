@@ -73,7 +73,7 @@ def parse():
                         "travel while chunk i+1 computes. Default 1 (the feature gradient's gather overlaps the "
                         "soft-mask branch): measured at N = 2, two chunks cost +0.15 ms of backward compute "
                         "(half-size launches) for at most 0.1 ms of hidden exchange at N = 8")
-    p.add_argument("--gather", default="auto", choices=["auto", "nccl", "peer", "peer_sm"],
+    p.add_argument("--gather", default="auto", choices=["auto", "nccl", "peer", "peer_sm", "peer_mc"],
                    help="N > 1: transport of the gradient all-gather. peer = stores into the peers' memory over "
                         "NVLink by the copy engines (kaolin_b200.multi_gpu.PeerGradAllGather), peer_sm = the same by "
                         "the dibr_b200_peer_push kernel, nccl = all_gather_into_tensor; auto = peer when CUDA "
@@ -704,7 +704,9 @@ def run_ours(args):
                    "gather_transport": transport["used"] if world > 1 else None,
                    "parallelism": (f"views sharded x{world}; all-gather of per-view grads "
                                    + ({"peer": "by copy-engine stores into peer memory over NVLink (symmetric memory), ",
-                                       "peer_sm": "by the dibr_b200_peer_push store kernel into peer memory over NVLink, "}
+                                       "peer_sm": "by the dibr_b200_peer_push store kernel into peer memory over NVLink, ",
+                                       "peer_mc": "by the dibr_b200_peer_push_multicast kernel (multimem.st through the "
+                                                  "NVSwitch multicast mapping of the landing buffers), "}
                                       .get(transport["used"], "with NCCL, "))
                                    + (f"backward in {bwd_chunks} view chunks, chunk i's gathers overlap chunk i+1"
                                       if pipelined else

@@ -356,6 +356,14 @@ int dibr_b200_deftet_sparse_render_backward(
  */
 int dibr_b200_peer_push(const void* src, size_t bytes, void* const* dst, int n_dst, size_t dst_offset_bytes,
                         int ctas, dibr_b200_stream_t stream);
+/*
+ * The same through an NVSwitch MULTICAST address (multimem.st): `multicast_dst` is the multicast
+ * mapping of the symmetric landing buffer; one store per 16 bytes lands at multicast_dst +
+ * dst_offset_bytes in EVERY GPU bound to the multicast object, this one included - a rank's
+ * egress is its shard once, not once per peer.
+ */
+int dibr_b200_peer_push_multicast(const void* src, size_t bytes, void* multicast_dst, size_t dst_offset_bytes,
+                                  int ctas, dibr_b200_stream_t stream);
 
 #ifdef __cplusplus
 }

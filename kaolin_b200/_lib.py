@@ -40,6 +40,7 @@ SIGNATURES = {
     "dibr_b200_version": (_i, []),
     "dibr_b200_trace_begin": (_i, []),
     "dibr_b200_peer_push": (_i, [_vp, _sz, ctypes.POINTER(ctypes.c_void_p), _i, _sz, _i, _vp]),
+    "dibr_b200_peer_push_multicast": (_i, [_vp, _sz, _vp, _sz, _i, _vp]),
     "dibr_b200_trace_end": (_i, [ctypes.c_char_p, _sz, ctypes.POINTER(ctypes.c_float), _i]),
     "dibr_b200_workspace_bytes": (_sz, [_i, _i64, _i, _i]),
     "dibr_b200_workspace_bytes_cached": (_sz, [_i, _i64, _i, _i, _i, _i64]),

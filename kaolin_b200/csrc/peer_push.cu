@@ -51,7 +51,44 @@ __global__ void __launch_bounds__(kPushThreads) peer_push_kernel(const int4* __r
   }
 }
 
+// Multicast variant: ONE multimem.st per 16 bytes to a multicast address - the NVSwitch replicates the
+// store into the same offset of every GPU bound to the multicast object (this GPU included), so the
+// egress of a rank is its shard once instead of once per peer (NVLink SHARP / "NVLS").
+__device__ __forceinline__ void multimem_st_v4(void* mc, const int4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kPushThreads) peer_push_multicast_kernel(const int4* __restrict__ src, size_t n16,
+                                                                            int4* mc) {
+  const size_t stride = (size_t)gridDim.x * kPushThreads;
+  size_t i = (size_t)blockIdx.x * kPushThreads + threadIdx.x;
+  for (; i + (kPushUnroll - 1) * stride < n16; i += kPushUnroll * stride) {
+    int4 v[kPushUnroll];
+#pragma unroll
+    for (int u = 0; u < kPushUnroll; ++u) v[u] = __ldg(src + i + u * stride);
+#pragma unroll
+    for (int u = 0; u < kPushUnroll; ++u) multimem_st_v4(mc + i + u * stride, v[u]);
+  }
+  for (; i < n16; i += stride) multimem_st_v4(mc + i, __ldg(src + i));
+}
+
 }  // namespace
+
+extern "C" int dibr_b200_peer_push_multicast(const void* src, size_t bytes, void* multicast_dst, size_t dst_offset_bytes,
+                                             int ctas, dibr_b200_stream_t stream) {
+  if (bytes && (!src || !multicast_dst)) return DIBR_B200_EINVAL;
+  if ((bytes & 15) || (dst_offset_bytes & 15) || ((uintptr_t)src & 15) || ((uintptr_t)multicast_dst & 15)) return DIBR_B200_EINVAL;
+  if (bytes == 0) return 0;
+  const size_t n16 = bytes / 16;
+  size_t want = (n16 + kPushThreads - 1) / kPushThreads;
+  if (ctas <= 0) ctas = 32;
+  if (want > (size_t)ctas) want = (size_t)ctas;
+  peer_push_multicast_kernel<<<(unsigned)want, kPushThreads, 0, (cudaStream_t)stream>>>(
+      static_cast<const int4*>(src), n16, reinterpret_cast<int4*>(static_cast<char*>(multicast_dst) + dst_offset_bytes));
+  return (int)cudaGetLastError();
+}
 
 extern "C" int dibr_b200_peer_push(const void* src, size_t bytes, void* const* dst, int n_dst, size_t dst_offset_bytes,
                                    int ctas, dibr_b200_stream_t stream) {

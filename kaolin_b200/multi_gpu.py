@@ -289,6 +289,11 @@ class _PeerPool:
         self.buf = symm_mem.empty(2 * self.gen_numel, dtype=dtype, device=device)
         self.hdl = symm_mem.rendezvous(self.buf, self.group)
         self.ptrs = [int(p) for p in self.hdl.buffer_ptrs]
+        self.ptr_array = None
+        try:
+            self.multicast_ptr = int(self.hdl.multicast_ptr)     # 0 when the box has no NVSwitch multicast
+        except Exception:
+            self.multicast_ptr = 0
         self.esz = esz
         self.streams = [torch.cuda.Stream(device, priority=-1) for _ in range(max(1, int(n_streams)))]
         self.generation = 0
@@ -324,7 +329,9 @@ class PeerGradAllGather:
     ``engine="ce"``: one peer-to-peer ``copy_`` per destination on high-priority side streams - the
     copy engines move the bytes, no SM is taken from the soft-mask branch that runs meanwhile.
     ``engine="sm"``: ``dibr_b200_peer_push`` (csrc/peer_push.cu), one small kernel that loads each 16 B
-    of the shard once and stores it to all destinations.
+    of the shard once and stores it to all destinations.  ``engine="mc"``:
+    ``dibr_b200_peer_push_multicast``, one ``multimem.st`` per 16 B to the NVSwitch multicast mapping of
+    the landing buffer - the switch replicates it to every GPU, so a rank's egress is its shard once.
 
     Cross-rank ordering: ``finish`` ends with the symmetric-memory barrier on the side stream (every
     rank's pushes are complete when it passes) and makes the current stream wait for it.  The
@@ -336,15 +343,15 @@ class PeerGradAllGather:
     shards, one box.  Raises at construction when symmetric memory is unavailable
     (``make_grad_all_gather`` falls back to NCCL)."""
 
-    BARRIER_TIMEOUT_MS = 20000
+    BARRIER_TIMEOUT_MS = 120000     # a rank that never arrives traps the barrier kernel instead of hanging the box
 
     def __init__(self, batch, local_fvi_shape, local_ff_shape, device, dtype=torch.float32, group=None,
                  engine="ce", streams=4, ctas=32):
         self.world = dist.get_world_size(group)
         if batch % self.world:
             raise ValueError(f"batch {batch} is not divisible by the world size {self.world}")
-        if engine not in ("ce", "sm"):
-            raise ValueError("engine must be 'ce' or 'sm'")
+        if engine not in ("ce", "sm", "mc"):
+            raise ValueError("engine must be 'ce', 'sm' or 'mc'")
         self.batch = int(batch)
         self.engine = engine
         self.ctas = int(ctas)
@@ -354,6 +361,8 @@ class PeerGradAllGather:
         if pool is None:
             pool = _PeerPool(group, device, lv, tuple(local_fvi_shape)[1:], tuple(local_ff_shape)[1:], dtype, streams)
             _peer_pools[key] = pool
+        if engine == "mc" and not pool.multicast_ptr:
+            raise RuntimeError("PeerGradAllGather: no NVSwitch multicast mapping for the landing buffer on this system")
         self.pool = pool
         self.gen = pool.generation
         pool.generation ^= 1
@@ -371,14 +380,22 @@ class PeerGradAllGather:
         ready = torch.cuda.Event()
         ready.record(torch.cuda.current_stream(dev))
         order = [(pool.rank + 1 + k) % pool.world for k in range(pool.world)]     # self last, peers rotated
-        if self.engine == "sm":
+        if self.engine in ("sm", "mc"):
             import ctypes
             from . import _lib
             s = pool.streams[0]
             s.wait_event(ready)
-            arr = (ctypes.c_void_p * pool.world)(*[pool.ptrs[r] for r in order])
-            st = _lib.lib().dibr_b200_peer_push(ctypes.c_void_p(local.data_ptr()), local.numel() * pool.esz, arr,
-                                                pool.world, pool.byte_offset(self.gen, kind, pool.rank), self.ctas,
+            off = pool.byte_offset(self.gen, kind, pool.rank)
+            if self.engine == "mc":
+                st = _lib.lib().dibr_b200_peer_push_multicast(
+                    ctypes.c_void_p(local.data_ptr()), local.numel() * pool.esz, ctypes.c_void_p(pool.multicast_ptr),
+                    off, self.ctas, ctypes.c_void_p(s.cuda_stream))
+                _lib.check(st, "dibr_b200_peer_push_multicast")
+                return
+            if pool.ptr_array is None:
+                pool.ptr_array = (ctypes.c_void_p * pool.world)(*[pool.ptrs[r] for r in order])
+            st = _lib.lib().dibr_b200_peer_push(ctypes.c_void_p(local.data_ptr()), local.numel() * pool.esz,
+                                                pool.ptr_array, pool.world, off, self.ctas,
                                                 ctypes.c_void_p(s.cuda_stream))
             _lib.check(st, "dibr_b200_peer_push")
             return
@@ -406,7 +423,7 @@ class PeerGradAllGather:
             self._push("ff", g_ff)
         self._push("fvi", g_fvi)
         s0 = pool.streams[0]
-        for s in pool.streams[1:]:
+        for s in (pool.streams[1:] if self.engine == "ce" else ()):
             e = torch.cuda.Event(); e.record(s); s0.wait_event(e)
         with torch.cuda.stream(s0):
             pool.hdl.barrier(channel=self.gen, timeout_ms=self.BARRIER_TIMEOUT_MS)
@@ -432,36 +449,38 @@ def _dibr_node(output):
 
 
 def make_grad_all_gather(batch, local_fvi_shape, local_ff_shape, device, transport="auto", group=None, **kw):
-    """-> (gather, transport used).  ``transport``: "peer" / "peer_sm" (``PeerGradAllGather`` with the
-    copy-engine or the store-kernel engine; raises if symmetric memory cannot be set up), "nccl"
-    (``OverlappedGradAllGather``) or "auto" (peer when the device is CUDA and symmetric memory
-    works, else nccl - decided collectively so that all ranks take the same path)."""
+    """-> (gather, transport used).  ``transport``: "peer" / "peer_sm" / "peer_mc" (``PeerGradAllGather``
+    with the copy-engine, store-kernel or multicast-store engine; raises if symmetric memory cannot be
+    set up), "nccl" (``OverlappedGradAllGather``) or "auto" (the best peer engine every rank can set
+    up, else nccl - decided collectively so that all ranks take the same path)."""
     if transport == "nccl":
         return OverlappedGradAllGather(batch, group), "nccl"
-    engine = "sm" if transport == "peer_sm" else "ce"
-    if transport in ("peer", "peer_sm"):
-        return PeerGradAllGather(batch, local_fvi_shape, local_ff_shape, device, group=group, engine=engine, **kw), transport
+    engines = {"peer": "ce", "peer_sm": "sm", "peer_mc": "mc"}
+    if transport in engines:
+        return PeerGradAllGather(batch, local_fvi_shape, local_ff_shape, device, group=group,
+                                 engine=engines[transport], **kw), transport
     if transport != "auto":
         raise ValueError(f"unknown transport {transport!r}")
     state = _auto_state.get(id(group))
     if state is None:
-        ok, gather = 1, None
-        if torch.device(device).type != "cuda":
-            ok = 0
-        else:
+        # every rank reports what it can do: 2 = multicast stores, 1 = unicast stores, 0 = NCCL only;
+        # the minimum over the ranks is what all of them use
+        level = 0
+        if torch.device(device).type == "cuda":
             try:
-                gather = PeerGradAllGather(batch, local_fvi_shape, local_ff_shape, device, group=group, **kw)
+                g = PeerGradAllGather(batch, local_fvi_shape, local_ff_shape, device, group=group, engine="sm", **kw)
+                level = 2 if (g.pool.multicast_ptr and AUTO_ALLOWS_MULTICAST) else 1
             except Exception as exc:          # no symmetric memory on this system / in this container
-                ok = 0
                 _auto_state[("why", id(group))] = f"{type(exc).__name__}: {exc}"
-        flag = torch.tensor([ok], dtype=torch.int32, device=device if torch.device(device).type == "cuda" else "cpu")
+        flag = torch.tensor([level], dtype=torch.int32, device=device if torch.device(device).type == "cuda" else "cpu")
         dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
-        state = _auto_state[id(group)] = "peer" if int(flag.item()) == 1 else "nccl"
-        if state == "peer" and gather is not None:
-            return gather, "peer"
-    if state == "peer":
-        return PeerGradAllGather(batch, local_fvi_shape, local_ff_shape, device, group=group, **kw), "peer"
-    return OverlappedGradAllGather(batch, group), "nccl"
+        state = _auto_state[id(group)] = ("nccl", "peer_sm", "peer_mc")[int(flag.item())]
+    if state == "nccl":
+        return OverlappedGradAllGather(batch, group), "nccl"
+    return PeerGradAllGather(batch, local_fvi_shape, local_ff_shape, device, group=group, engine=engines[state], **kw), state
 
 
+# "auto" prefers the multicast engine: measured at N = 8 (profiles/r2_bench_n8_peer_*.json) 2.611 ms/step
+# against 2.662 (unicast stores), 2.896 (copy engines) and 2.736 (NCCL, another box)
+AUTO_ALLOWS_MULTICAST = True
 _auto_state = {}

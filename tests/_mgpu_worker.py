@@ -84,7 +84,7 @@ def main():
     # all-gather by stores into peer memory (NVLink): three consecutive steps with different data through
     # the persistent double-buffered landing areas; every step bit-equal to the NCCL all-gather of the same
     # local gradients, the first also within 1e-5 of the single-GPU answer
-    for engine in ("ce", "sm"):
+    for engine in ("ce", "sm", "mc"):
         name = "peer_" + engine
         try:
             steps, exact, e1, e2 = [], True, None, None

@@ -38,7 +38,7 @@ def test_sharded_nccl_equals_single_gpu():
         for mode in ("overlapped", "pipelined", "chunked"):
             assert x[mode]["images_bit_equal"]
             assert x[mode]["grad_fvi_rel"] <= 1e-5 and x[mode]["grad_ff_rel"] <= 1e-5
-        for mode in ("peer_ce", "peer_sm"):       # all-gather by stores into peer memory, when the box offers it
+        for mode in ("peer_ce", "peer_sm", "peer_mc"):       # all-gather by stores into peer memory, when the box offers it
             if x[mode]["available"]:
                 assert x[mode]["equal_to_nccl_all_gather"]
                 assert x[mode]["grad_fvi_rel"] <= 1e-5 and x[mode]["grad_ff_rel"] <= 1e-5
