@@ -539,7 +539,9 @@ def run_ours(args):
             host_out[slot][0].copy_(st_fvi, non_blocking=True)
             host_out[slot][1].copy_(st_ff, non_blocking=True)
             host_out[slot][2].copy_(st_loss, non_blocking=True)
-            ev = torch.cuda.Event(); ev.record(s_d2h)
+            # blocking=True: the host SLEEPS in ev_read.synchronize() instead of spinning - with one process per
+            # GPU under a CPU quota (8 ranks on a 16-CPU cgroup) eight spinning waiters starve the autograd threads
+            ev = torch.cuda.Event(blocking=True); ev.record(s_d2h)
         ev_read[slot] = ev
         state["i"] = i + 1
 

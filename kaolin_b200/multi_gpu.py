@@ -339,8 +339,9 @@ class PeerGradAllGather:
     valid until the ``finish`` after the next one, provided they are consumed on the current stream
     (a rank starts pushing generation g+2 only after its own consumer of generation g, which
     precedes its next backward in stream order, and after every rank passed barrier g+1).
-    Same interface as ``OverlappedGradAllGather`` (``hook`` / ``attach`` / ``finish``); equal
-    shards, one box.  Raises at construction when symmetric memory is unavailable
+    One gather per (group, gradient shapes) is in flight at a time (``finish`` it before the next
+    backward pushes).  Same interface as ``OverlappedGradAllGather`` (``hook`` / ``attach`` /
+    ``finish``); equal shards, one box.  Raises at construction when symmetric memory is unavailable
     (``make_grad_all_gather`` falls back to NCCL)."""
 
     BARRIER_TIMEOUT_MS = 120000     # a rank that never arrives traps the barrier kernel instead of hanging the box
@@ -364,8 +365,7 @@ class PeerGradAllGather:
         if engine == "mc" and not pool.multicast_ptr:
             raise RuntimeError("PeerGradAllGather: no NVSwitch multicast mapping for the landing buffer on this system")
         self.pool = pool
-        self.gen = pool.generation
-        pool.generation ^= 1
+        self.gen = None          # taken at the first push: an object that is created and dropped uses no generation
         self.keep = []
         self.pushed_ff = False
 
@@ -374,6 +374,9 @@ class PeerGradAllGather:
         if tuple(local.shape) != pool.shapes[kind] or local.dtype != pool.dtype:
             raise ValueError(f"PeerGradAllGather: {kind} shard is {tuple(local.shape)} {local.dtype}, "
                              f"expected {pool.shapes[kind]} {pool.dtype}")
+        if self.gen is None:
+            self.gen = pool.generation
+            pool.generation ^= 1
         local = local.contiguous()
         self.keep.append(local)               # alive until finish(): the side streams read it
         dev = pool.device

@@ -104,6 +104,8 @@ def forward(mode, height, width, fvz, fvi, ff, fnz, valid_u8, multiplier, eps,
     wts = torch.empty((B, height, width, 3), dtype=torch.float32, device=dev) if raster else None
     idx = torch.empty((B, height, width), dtype=torch.int64, device=dev) if raster else face_idx_in
     soft = torch.empty((B, height, width), dtype=torch.float32, device=dev) if soft_on else None
+    if B == 0:       # an empty view shard (batch < world size): empty images, nothing to launch
+        return feat, idx, wts, soft, None
     ws = workspace(B, B * F, height, width, dev, knum if soft_on else 0)
     with torch.cuda.device(dev):
         fn = _lib.lib().dibr_b200_forward_bf16 if bf16 else _lib.lib().dibr_b200_forward
@@ -200,6 +202,8 @@ def forward_f64(mode, height, width, fvz, fvi, ff, fnz, valid_u8, multiplier, ep
     wts = torch.empty((B, height, width, 3), dtype=f64, device=dev) if raster else None
     idx = torch.empty((B, height, width), dtype=torch.int64, device=dev) if raster else face_idx_in
     soft = torch.empty((B, height, width), dtype=f64, device=dev) if soft_on else None
+    if B == 0:
+        return feat, idx, wts, soft, None
     n = _lib.lib().dibr_b200_workspace_bytes_f64(B, B * F, height, width)
     if n == 0:
         raise RuntimeError("kaolin_b200: unsupported problem size")

@@ -602,6 +602,19 @@ def test_empty_mesh():
     assert (soft == 0).all()
 
 
+def test_empty_view_shard():
+    """batch < world size leaves a rank with zero views (multi_gpu.shard_range): empty outputs and gradients."""
+    fvz, fvi, fnz = synthetic.icosphere_views(1, 1, seed=1)
+    ff = synthetic.random_features(1, fvz.shape[1], 2)
+    for dt in (torch.float32, torch.float64):
+        t_fvi, t_ff = T(fvi)[:0].to(dt).requires_grad_(True), T(ff)[:0].to(dt).requires_grad_(True)
+        feat, soft, idx = dibr_rasterization(24, 32, T(fvz)[:0].to(dt), t_fvi, t_ff, T(fnz)[:0].to(dt))
+        assert feat.shape == (0, 24, 32, 2) and soft.shape == (0, 24, 32) and idx.shape == (0, 24, 32)
+        assert feat.dtype == dt and idx.dtype == torch.int64
+        (feat.sum() + soft.sum()).backward()
+        assert t_fvi.grad.shape == t_fvi.shape and t_ff.grad.shape == t_ff.shape
+
+
 def test_errors_like_reference():
     fvz, fvi, fnz = synthetic.icosphere_views(1, 1, seed=1)
     ff = synthetic.random_features(1, fvz.shape[1], 2)
