@@ -143,3 +143,49 @@ def test_double_edge_cases():
     fvz, fvi, fnz, ff = _scene(1, 1, 97)
     feat, soft, idx = dibr_rasterization(16, 16, D(fvz), D(fvi), D(ff), -torch.ones_like(D(fnz)))
     assert (idx == -1).all() and (feat == 0).all()
+
+
+def _mask_iou(soft, face_idx):
+    """kaolin/metrics/render.py:18-41 with the shifted target of test_dibr.py:182-186."""
+    mask = (face_idx != -1).to(soft.dtype)
+    shifted = torch.nn.functional.pad(mask, (0, 5))[..., 5:]
+    B = soft.shape[0]
+    mul = soft * shifted
+    add = soft + shifted
+    up = torch.sum(mul.reshape(B, -1), dim=1)
+    down = torch.sum((add - mul).reshape(B, -1), dim=1)
+    return 1.0 - torch.mean(up / (down + 1e-10))
+
+
+@pytest.mark.parametrize("fixture", ["dibr_simple", "dibr_sphere"])
+def test_double_on_the_reference_fixtures(golden_dir, fixture):
+    """The reference runs its fixture tests in torch.double too (test_dibr.py:37, 109-191, 309-394) against
+    the SAME stored values: double results agree with the float goldens to the goldens' own rounding
+    (1e-4 here), and with the reference's double kernels exactly / to 1e-9."""
+    import os
+    from kaolin_b200.render.mesh import rasterize, dibr_soft_mask
+    g = np.load(os.path.join(golden_dir, fixture + ".npz"))
+    key = "s7000_b0.02_"
+    H, W = 35, 31
+    fvi, fvz = D(g["fvi"]), D(g["fvz"])
+    ff = torch.zeros(tuple(fvz.shape) + (1,), device=DEV, dtype=torch.float64)
+    _, face_idx = rasterize(H, W, fvz, fvi, ff)
+    if "face_idx" in g.files:
+        assert torch.equal(face_idx.cpu(), torch.from_numpy(g["face_idx"].astype(np.int64)))
+    t = fvi.clone().requires_grad_(True)
+    soft = dibr_soft_mask(t, face_idx, 7000, 0.02, 30, 1000)
+    assert soft.dtype == torch.float64
+    gt_soft = torch.from_numpy(g[key + "soft_mask"]).to(DEV).double()
+    assert float((soft - gt_soft).abs().max()) <= 1e-4
+    _mask_iou(soft, face_idx).backward()
+    if fixture == "dibr_simple":           # (the sphere's stored gradient is only good to 1e-1, test_dibr.py:392)
+        gt_grad = torch.from_numpy(g[key + "grad_fvi"]).to(DEV).double()
+        assert torch.allclose(t.grad, gt_grad, rtol=1e-4, atol=1e-4)
+    from oracle import ref_cuda
+    if ref_cuda.available():
+        r_soft, fvi_m, prob, cidx, ctype = ref_cuda.soft_mask_forward(fvi, face_idx, 7000, 0.02, 30, 1000.)
+        assert float((soft - r_soft).abs().max()) <= 1e-10
+        s_req = r_soft.clone().requires_grad_(True)
+        _mask_iou(s_req, face_idx).backward()
+        r_g = ref_cuda.soft_mask_backward(s_req.grad, r_soft, face_idx, prob, cidx, ctype, fvi_m, 7000, 1000.)
+        assert rel(t.grad, r_g) <= 1e-9
