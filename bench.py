@@ -10,7 +10,8 @@ faces, jittered, random rotation and camera; SURVEY.md §8d generator G1) at
 1024x1024, D = 3 feature channels, fp32.  One "step" = dibr_rasterization forward
 + backward (grads wrt face_vertices_image and face_features) over the shard;
 with N > 1 every rank renders its own 32 views (weak scaling) and the per-view
-gradients are all-gathered with NCCL.  Prints ONE JSON line on rank 0.
+gradients are all-gathered (--gather: stores into peer memory over NVLink when
+the box offers symmetric memory, else NCCL).  Prints ONE JSON line on rank 0.
 """
 import argparse
 import json
