@@ -53,6 +53,25 @@ def test_workspace_query_and_host_side_errors():
     assert st == _lib.ESIZE
     with pytest.raises(RuntimeError):
         _lib.check(st, "dibr_b200_forward")
+    # float64 entry points: same host-side contract
+    n64 = lib.dibr_b200_workspace_bytes_f64(4, 4 * 20480, 1024, 1024)
+    assert 0 < n64 < 200e6
+    assert lib.dibr_b200_workspace_bytes_f64(0, 10, 64, 64) == 0
+    st = lib.dibr_b200_forward_f64(1, 4, 8, 8, 1, None, None, None, None, None, 1000.0, 1e-8, 3,
+                                   7000.0, 20.0, 30, None, None, None, None, None, 0, None)
+    assert st == _lib.EINVAL
+    st = lib.dibr_b200_backward_f64(1, 4, 20000, 8, 1, None, None, None, None, None, None, None,
+                                    1000.0, 1e-8, 7000.0, 20.0, 30, None, None, None, 0, 0, None)
+    assert st == _lib.ESIZE
+    # peer push: argument errors are host-side
+    import ctypes
+    arr = (ctypes.c_void_p * 1)(ctypes.c_void_p(4096))
+    assert lib.dibr_b200_peer_push(None, 32, arr, 1, 0, 0, None) == _lib.EINVAL           # no source
+    assert lib.dibr_b200_peer_push(ctypes.c_void_p(4096), 24, arr, 1, 0, 0, None) == _lib.EINVAL   # not 16-byte units
+    assert lib.dibr_b200_peer_push(ctypes.c_void_p(4096), 32, arr, 17, 0, 0, None) == _lib.EINVAL  # > 16 destinations
+    assert lib.dibr_b200_peer_push(ctypes.c_void_p(4096), 0, arr, 1, 0, 0, None) == 0              # nothing to do
+    assert lib.dibr_b200_peer_push_multicast(ctypes.c_void_p(4096), 32, None, 0, 0, None) == _lib.EINVAL
+    assert lib.dibr_b200_peer_push_multicast(ctypes.c_void_p(4096), 32, ctypes.c_void_p(4104), 0, 0, None) == _lib.EINVAL
 
 
 def test_python_signatures_match_reference():
