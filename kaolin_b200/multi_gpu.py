@@ -162,17 +162,7 @@ class OverlappedGradAllGather:
     def attach(self, output):
         """Registers the hook on the autograd node that produced ``output`` (the soft mask
         or the features of ONE ``dibr_rasterization`` call).  Returns self."""
-        node = getattr(output, "grad_fn", None)
-        seen = 0
-        while node is not None and not type(node).__name__.startswith("DibrRasterizationB200") and seen < 4:
-            # e.g. a slice of the feature image (list/tuple face_features): step to its producer
-            nxt = [fn for fn, _ in node.next_functions if fn is not None]
-            node = nxt[0] if len(nxt) == 1 else None
-            seen += 1
-        if node is None or not type(node).__name__.startswith("DibrRasterizationB200"):
-            raise ValueError("attach() needs an output of kaolin_b200.render.mesh.dibr_rasterization "
-                             "that requires grad")
-        node.feature_grad_hook = self.hook
+        _dibr_node(output).feature_grad_hook = self.hook
         return self
 
     def finish(self, g_fvi, g_ff=None):
@@ -241,16 +231,7 @@ class PipelinedGradAllGather:
         self.result = pipelined_backward_all_gather(local_views, self.chunks, run_chunk, g_fvi, g_ff, self.group)
 
     def attach(self, output):
-        node = getattr(output, "grad_fn", None)
-        seen = 0
-        while node is not None and not type(node).__name__.startswith("DibrRasterizationB200") and seen < 4:
-            nxt = [fn for fn, _ in node.next_functions if fn is not None]
-            node = nxt[0] if len(nxt) == 1 else None
-            seen += 1
-        if node is None or not type(node).__name__.startswith("DibrRasterizationB200"):
-            raise ValueError("attach() needs an output of kaolin_b200.render.mesh.dibr_rasterization "
-                             "that requires grad")
-        node.view_pipeline = self._run
+        _dibr_node(output).view_pipeline = self._run
         return self
 
     def finish(self):
@@ -438,14 +419,20 @@ class PeerGradAllGather:
         return full_fvi, full_ff
 
 
+_DIBR_NODES = ("DibrRasterizationB200", "DibrRasterizationF64")     # render/mesh/dibr.py: fp32 / float64 node
+
+
 def _dibr_node(output):
+    """The autograd node of the ``dibr_rasterization`` call (fp32 or float64) that produced ``output``."""
+    is_dibr = lambda n: type(n).__name__.startswith(_DIBR_NODES)
     node = getattr(output, "grad_fn", None)
     seen = 0
-    while node is not None and not type(node).__name__.startswith("DibrRasterizationB200") and seen < 4:
+    while node is not None and not is_dibr(node) and seen < 4:
+        # e.g. a slice of the feature image (list/tuple face_features): step to its producer
         nxt = [fn for fn, _ in node.next_functions if fn is not None]
         node = nxt[0] if len(nxt) == 1 else None
         seen += 1
-    if node is None or not type(node).__name__.startswith("DibrRasterizationB200"):
+    if node is None or not is_dibr(node):
         raise ValueError("attach() needs an output of kaolin_b200.render.mesh.dibr_rasterization "
                          "that requires grad")
     return node

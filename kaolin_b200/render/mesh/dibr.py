@@ -94,6 +94,11 @@ class DibrRasterizationF64(Function):
         g_soft = None if grad_soft_mask is None else grad_soft_mask.contiguous()
         g_fvi, g_ff = _host.backward_f64(height, width, g_feat, g_soft, face_idx, wts, soft, fvi, ff, multiplier, eps,
                                          sigmainv, boxlen_m, knum, ctx.ws)
+        # per-node hook of the multi-GPU gathers (multi_gpu.*.attach); the float64 backward is one kernel, so the
+        # feature gradient is handed over at the end instead of between the branches
+        hook = getattr(ctx, "feature_grad_hook", None)
+        if hook is not None and g_feat is not None and g_soft is not None:
+            hook(g_ff)
         return None, None, None, g_fvi, g_ff, None, None, None, None, None, None, None
 
 

@@ -182,3 +182,37 @@ def test_two_rank_gloo_pipelined_backward_gather(batch, chunks):
     port = 35500 + (os.getpid() % 2000) + batch * 8 + chunks
     mp.spawn(_pipelined_worker, args=(2, batch, chunks, port, ok), nprocs=2, join=True)
     assert list(ok) == [1, 1]
+
+
+def test_attach_finds_the_dibr_node_through_a_slice():
+    """attach() walks from an output (or a slice of it: list/tuple face_features) to the autograd node of the
+    dibr_rasterization call, recognised by its class name, and stores the hook on THAT node only."""
+    from kaolin_b200 import multi_gpu
+
+    class DibrRasterizationB200(torch.autograd.Function):     # stands in for render/mesh/dibr.py's node on CPU
+        @staticmethod
+        def forward(ctx, x):
+            return x * 2.0
+
+        @staticmethod
+        def backward(ctx, g):
+            return g * 2.0
+
+    x = torch.ones(4, 3, requires_grad=True)
+    out = DibrRasterizationB200.apply(x)
+    node = multi_gpu._dibr_node(out[..., :2])
+    assert node is out.grad_fn
+    other = DibrRasterizationB200.apply(x)
+    g = object.__new__(multi_gpu.OverlappedGradAllGather)      # no process group needed for attach()
+    g.hook = lambda t: None
+    assert g.attach(out) is g
+    assert out.grad_fn.feature_grad_hook is g.hook and not hasattr(other.grad_fn, "feature_grad_hook")
+    class DibrRasterizationF64(DibrRasterizationB200):         # the float64 node is recognised as well
+        pass
+
+    out64 = DibrRasterizationF64.apply(x)
+    assert multi_gpu._dibr_node(out64) is out64.grad_fn
+    with pytest.raises(ValueError):
+        multi_gpu._dibr_node(x * 3.0)
+    with pytest.raises(ValueError):
+        multi_gpu._dibr_node(torch.ones(3))
