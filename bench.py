@@ -729,7 +729,9 @@ def run_ours(args):
                                 "downloads them too",
                 "host_wall_ms_per_step": wall_ms / args.steps},
         "e2e_images": e2e_images, "e2e_graphed": e2e_graphed,
-        "gpu_launches": max(1, len(kernel_order)) * len(spans) * args.steps,   # kernels per (chunk of a) step, as traced
+        # kernels per (chunk of a) step, as traced, + the two push kernels of the peer-memory all-gather
+        "gpu_launches": (max(1, len(kernel_order)) * len(spans)
+                         + (2 if transport["used"] in ("peer_sm", "peer_mc") else 0)) * args.steps,
         "roofline": roofline,
         "triangle_pixel_tests_per_s": {
             "brute_force_equivalent": float(B) * H * W * F * 0.5 / (fwd_ms * 1e-3),
